@@ -1,0 +1,220 @@
+/*
+ * tlod_b200.h -- C ABI of libtlod_b200.so: the Faster R-CNN RoI / proposal hot
+ * path of live-group/Transfer-Learning-Library-for-Object-Detection as
+ * hand-written CUDA for sm_100a (B200).
+ *
+ * This is the drop-in boundary.  Every entry point replaces one symbol the
+ * reference binds through its cffi bridge (`torch.utils.ffi`), cited per
+ * function as /root/reference path:line.  Conventions (same as the reference's
+ * tensor-free launcher layer, lib/model/roi_align/src/roi_align_kernel.h:13-27):
+ *
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless it
+ *     is named `h_*`; all tensors are contiguous, fp32 NCHW, int32 indices;
+ *   - the CALLER allocates everything, including outputs and workspaces (query
+ *     the `*_workspace_bytes` functions); the library never frees or retains;
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default
+ *     stream).  All work is enqueued on it; no entry point synchronises the
+ *     host, reads device memory from the host, or allocates device memory;
+ *   - return value: 0 = success; < 0 = TLOD_ERR_* argument error (nothing was
+ *     launched); > 0 = the `cudaError_t` of the failed launch.  The library
+ *     never calls exit() (the reference does: roi_align_kernel.cu:84-88);
+ *   - re-entrant and device-correct: kernels run on the device that is current
+ *     for the calling thread, like the reference under nn.DataParallel.
+ *
+ * There is no CPU implementation behind any of these symbols.
+ */
+#ifndef TLOD_B200_H
+#define TLOD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TLOD_B200_VERSION 100 /* 0.1.0 */
+
+enum {
+  TLOD_OK = 0,
+  TLOD_ERR_NULL_POINTER = -1,
+  TLOD_ERR_BAD_SHAPE = -2,      /* non-positive or inconsistent sizes            */
+  TLOD_ERR_UNSUPPORTED = -3,    /* valid request outside the implemented range   */
+  TLOD_ERR_WORKSPACE = -4,      /* workspace missing or too small                */
+  TLOD_ERR_INT32_OVERFLOW = -5  /* tensor has >= 2^31 elements (reference: UB)   */
+};
+
+int tlod_version(void);
+/* Static string for a TLOD_ERR_* code or a cudaError_t. */
+const char* tlod_error_string(int code);
+/* Number of kernel launches enqueued by this library in this process (bench.py's `gpu_launches`). */
+unsigned long long tlod_launch_count(void);
+
+/* ------------------------------------------------------------------------ */
+/* RoIAlign                                                                   */
+/* replaces roi_align_forward_cuda / roi_align_backward_cuda                  */
+/*   lib/model/roi_align/src/roi_align_cuda.c:7-40, :42-76                    */
+/*   (kernels lib/model/roi_align/src/roi_align_kernel.cu:15-70, :94-143)     */
+/* ------------------------------------------------------------------------ */
+/* features (batch, channels, height, width); rois (num_rois, 5) =
+ * [batch_idx, x1, y1, x2, y2] in image pixels; output (num_rois, channels,
+ * aligned_h, aligned_w).  One bilinear sample per output cell at
+ * start + p * extent/(aligned-1); see SURVEY.md appendix B items 1-7.
+ * Every output element is written (RoIs whose batch index is outside
+ * [0, batch) produce zeros; the reference reads out of bounds there).
+ * Requires height >= 2, width >= 2, aligned_h >= 2, aligned_w >= 2. */
+int tlod_roi_align_forward(const float* features, const float* rois, float* output, int batch,
+                           int channels, int height, int width, int num_rois, int aligned_h,
+                           int aligned_w, float spatial_scale, void* stream);
+
+/* top_grad (num_rois, channels, aligned_h, aligned_w) -> bottom_grad (batch,
+ * channels, height, width).  bottom_grad is fully OVERWRITTEN with the gradient
+ * (the reference accumulates into a buffer its caller has just zeroed,
+ * functions/roi_align.py:42, so the observable result is the same). */
+int tlod_roi_align_backward(const float* top_grad, const float* rois, float* bottom_grad,
+                            int batch, int channels, int height, int width, int num_rois,
+                            int aligned_h, int aligned_w, float spatial_scale, void* stream);
+
+/* ------------------------------------------------------------------------ */
+/* RoIPool                                                                    */
+/* replaces roi_pooling_forward_cuda / roi_pooling_backward_cuda              */
+/*   lib/model/roi_pooling/src/roi_pooling_cuda.c                             */
+/*   (kernels lib/model/roi_pooling/src/roi_pooling_kernel.cu:24-93, :128-203)*/
+/* ------------------------------------------------------------------------ */
+/* argmax (num_rois, channels, pooled_h, pooled_w) int32: flat index into the
+ * whole features buffer, -1 for an empty bin; may be NULL. */
+int tlod_roi_pool_forward(const float* features, const float* rois, float* output, int* argmax,
+                          int batch, int channels, int height, int width, int num_rois,
+                          int pooled_h, int pooled_w, float spatial_scale, void* stream);
+
+/* bottom_grad fully overwritten.  Reproduces the reference gather exactly up
+ * to fp32 summation order: a top_grad element is counted only if its argmax
+ * cell lies inside the rounded RoI and inside the bin's feasible set
+ * (roi_pooling_kernel.cu:157-196). */
+int tlod_roi_pool_backward(const float* top_grad, const int* argmax, const float* rois,
+                           float* bottom_grad, int batch, int channels, int height, int width,
+                           int num_rois, int pooled_h, int pooled_w, float spatial_scale,
+                           void* stream);
+
+/* ------------------------------------------------------------------------ */
+/* NMS                                                                        */
+/* replaces nms_cuda                lib/model/nms/src/nms_cuda.c:8-19         */
+/*   (nms_kernel + host greedy scan lib/model/nms/src/nms_cuda_kernel.cu:41-161)*/
+/* ------------------------------------------------------------------------ */
+/* boxes: n rows of `box_stride` floats (>= 4; the reference passes 5 =
+ * x1 y1 x2 y2 score), already sorted by score descending.  IoU uses the
+ * reference's fp32 formula with every operation individually rounded
+ * (no FMA contraction); a box is suppressed iff IoU > thresh (strict).
+ * keep_out[0 .. *num_out) = ascending kept indices, both on the DEVICE; no host
+ * synchronisation happens inside (the reference does 4).  max_keep > 0 stops
+ * after that many survivors (the caller's `[:post_nms_topN]`).
+ * workspace: tlod_nms_workspace_bytes(n) bytes, 16-byte aligned. */
+size_t tlod_nms_workspace_bytes(int n);
+int tlod_nms(const float* boxes, int n, int box_stride, float thresh, int max_keep, int* keep_out,
+             int* num_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------ */
+/* Proposal layer (fused, batched)                                            */
+/* replaces _ProposalLayer.forward     lib/model/rpn/proposal_layer.py:49-163 */
+/*   = bbox_transform_inv + clip_boxes lib/model/rpn/bbox_transform.py:77-133 */
+/*   + torch.sort + per-image nms() + padding                                 */
+/* ------------------------------------------------------------------------ */
+/* scores (batch, 2A, H, W): fg probabilities are channels [A, 2A);
+ * deltas (batch, 4A, H, W); im_info (batch, 3) = [h, w, scale];
+ * anchors (A, 4) base anchors (generate_anchors output as fp32);
+ * rois_out (batch, post_nms_topN, 5): zero padded, column 0 = image index.
+ * pre_nms_topN is applied only if 0 < pre_nms_topN < batch*H*W*A (the
+ * reference's whole-batch numel test, proposal_layer.py:138).
+ * Optional debug outputs (may be NULL): order_out (batch, n_sorted) int32 flat
+ * anchor index per rank; sorted_boxes_out (batch, n_sorted, 4); num_out (batch).
+ * Ties in score keep the lower anchor index first (stable descending sort). */
+int tlod_proposals_n_sorted(int batch, int num_anchors, int height, int width, int pre_nms_topN);
+size_t tlod_proposals_workspace_bytes(int batch, int num_anchors, int height, int width,
+                                      int pre_nms_topN, int post_nms_topN);
+int tlod_proposals(const float* scores, const float* deltas, const float* im_info,
+                   const float* anchors, float* rois_out, int batch, int num_anchors, int height,
+                   int width, int feat_stride, int pre_nms_topN, int post_nms_topN,
+                   float nms_thresh, int* order_out, float* sorted_boxes_out, int* num_out,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------ */
+/* Box arithmetic used by the RPN / test scripts                              */
+/*   lib/model/rpn/bbox_transform.py:36-75, :77-103, :125-133, :168-257       */
+/* ------------------------------------------------------------------------ */
+/* boxes (batch, n, 4) [or (n,4) shared by all images when boxes_batched == 0],
+ * deltas (batch, n, 4) -> out (batch, n, 4); then clip to im_info if non-NULL. */
+int tlod_bbox_transform_inv_clip(const float* boxes, int boxes_batched, const float* deltas,
+                                 const float* im_info, float* out, int batch, int n, void* stream);
+/* in-place clip_boxes: boxes (batch, n, 4*k) clamped to [0, w-1] x [0, h-1] */
+int tlod_clip_boxes(float* boxes, const float* im_info, int batch, int n, int k, void* stream);
+/* overlaps (batch, n, k): anchors (n,4) if anchors_batched == 0 else
+ * (batch, n, anchor_stride) with the 4 coordinates at column anchor_offset;
+ * gt (batch, k, gt_stride).  gt with w==h==1 -> 0, anchor with w==h==1 -> -1. */
+int tlod_bbox_overlaps_batch(const float* anchors, int anchors_batched, int anchor_stride,
+                             int anchor_offset, const float* gt, int gt_stride, float* overlaps,
+                             int batch, int n, int k, void* stream);
+/* targets (batch, n, 4) = (dx, dy, log dw, log dh); ex (n,4) or (batch,n,4). */
+int tlod_bbox_transform_batch(const float* ex_rois, int ex_batched, const float* gt_rois,
+                              float* targets, int batch, int n, void* stream);
+
+/* ------------------------------------------------------------------------ */
+/* Anchor-target assignment                                                   */
+/* replaces the device part of _AnchorTargetLayer.forward                     */
+/*   lib/model/rpn/anchor_target_layer.py:98-116 (labels), :147-191 (targets) */
+/* The random subsampling (:123-145) stays on the host, as in the reference.  */
+/* ------------------------------------------------------------------------ */
+/* anchors (n, 4) inside-image anchors; gt (batch, k, gt_stride>=4).
+ * labels (batch, n) fp32 in {-1, 0, 1}; argmax (batch, n) int32 (ties -> lowest
+ * gt index); max_overlaps (batch, n) or NULL.
+ * workspace: tlod_anchor_labels_workspace_bytes(batch, k). */
+size_t tlod_anchor_labels_workspace_bytes(int batch, int k);
+int tlod_anchor_labels(const float* anchors, const float* gt, int gt_stride, float* labels,
+                       int* argmax, float* max_overlaps, int batch, int n, int k,
+                       float negative_overlap, float positive_overlap, int clobber_positives,
+                       void* workspace, size_t workspace_bytes, void* stream);
+/* Final maps.  labels/argmax (batch, n) over inside anchors (after the host
+ * subsampling); inv_index (total) int32: position of each of the total = H*W*A
+ * anchors in the inside list or -1.
+ * Outputs in the reference's layouts: labels_out (batch, 1, A*H, W),
+ * targets_out / inside_w_out / outside_w_out (batch, 4A, H, W). */
+int tlod_anchor_targets_finalize(const float* labels, const int* argmax, const float* anchors,
+                                 const float* gt, int gt_stride, const int* inv_index,
+                                 float* labels_out, float* targets_out, float* inside_w_out,
+                                 float* outside_w_out, int batch, int n, int k, int num_anchors,
+                                 int height, int width, float inside_weight,
+                                 float positive_weight, float negative_weight, void* stream);
+
+/* ------------------------------------------------------------------------ */
+/* Gradient reversal + domain-classifier loss reduction                       */
+/*   lib/DAF/DA.py:19-33 (GRLayer), lib/MAF/DA.py:34-53 (weighted GRL),       */
+/*   lib/DAF/faster_rcnn.py:181-220 (image / instance / consistency losses)   */
+/* ------------------------------------------------------------------------ */
+/* out[i] = -alpha * grad[i]  (one kernel instead of neg() and mul()) */
+int tlod_grl_backward(const float* grad, float* out, float alpha, long long n, void* stream);
+/* out[r, :] = -alpha * weight[r] * grad[r, :]   grad (rows, cols) */
+int tlod_grl_backward_weighted(const float* grad, const float* row_weight, float* out, float alpha,
+                               int rows, int cols, void* stream);
+/* img_score (batch, 2, H, W) logits, ins_prob (num_ins) sigmoid outputs,
+ * ins_label (num_ins) or NULL (= domain_label everywhere), domain_label 0/1.
+ * losses_out[4] = { image NLL (mean), instance BCE (mean), consistency MSE
+ * (sum, target = mean softmax prob of channel domain_label, detached),
+ * consistency target }.  workspace: tlod_da_loss_workspace_bytes(). */
+size_t tlod_da_loss_workspace_bytes(void);
+int tlod_da_loss_forward(const float* img_score, const float* ins_prob, const float* ins_label,
+                         int domain_label, float* losses_out, int batch, int height, int width,
+                         int num_ins, void* workspace, size_t workspace_bytes, void* stream);
+/* Gradients of w_img*img + w_ins*ins + w_cst*cst given losses_out from the
+ * forward call: grad_img_score (batch,2,H,W), grad_ins_prob (num_ins).
+ * upstream (3 floats on the DEVICE, may be NULL): autograd's incoming gradients of
+ * the three losses, multiplied into the weights on the device so that the
+ * caller never has to read them back. */
+int tlod_da_loss_backward(const float* img_score, const float* ins_prob, const float* ins_label,
+                          int domain_label, const float* losses_out, const float* upstream,
+                          float w_img, float w_ins, float w_cst, float* grad_img_score,
+                          float* grad_ins_prob, int batch, int height, int width, int num_ins,
+                          void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TLOD_B200_H */

@@ -1,0 +1,109 @@
+"""_AnchorTargetLayer (lib/model/rpn/anchor_target_layer.py:31-219).
+
+Same constructor and forward((rpn_cls_score, gt_boxes, im_info, num_boxes)) -> list of
+[labels (B,1,A*H,W), bbox_targets, bbox_inside_weights, bbox_outside_weights (B,4A,H,W)].
+
+Device work is two fused passes (tlod_anchor_labels: IoU + per-gt max + label rules, no
+(B,N,K) tensor; tlod_anchor_targets_finalize: targets + weights + unmap + permute).  The
+random subsampling stays on the host with numpy's global RNG, consumed in exactly the
+reference's order (:123-145), because the RNG stream position is data dependent."""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from model.utils.config import cfg
+from tlod_b200 import functional as F
+
+from .generate_anchors import generate_anchors
+
+
+class _AnchorTargetLayer(nn.Module):
+    def __init__(self, feat_stride, scales, ratios):
+        super(_AnchorTargetLayer, self).__init__()
+        self._feat_stride = feat_stride
+        self._scales = scales
+        self._anchors_np = generate_anchors(scales=np.array(scales), ratios=np.array(ratios)).astype(np.float32)
+        self._anchors = torch.from_numpy(self._anchors_np)
+        self._num_anchors = self._anchors.size(0)
+        self._allowed_border = 0
+        self._cache = {}
+
+    def _inside(self, feat_h, feat_w, lim_w, lim_h, device):
+        """Inside-image anchors for this map size (:66-91): (anchors (n,4), inds (n,), inverse (total,))."""
+        key = (feat_h, feat_w, lim_w, lim_h, str(device))
+        hit = self._cache.get(key)
+        if hit is None:
+            sx = (np.arange(0, feat_w) * self._feat_stride).astype(np.float32)
+            sy = (np.arange(0, feat_h) * self._feat_stride).astype(np.float32)
+            gx, gy = np.meshgrid(sx, sy)
+            shifts = np.stack((gx.ravel(), gy.ravel(), gx.ravel(), gy.ravel()), axis=1)
+            all_anchors = (self._anchors_np[None, :, :] + shifts[:, None, :]).reshape(-1, 4)
+            b = self._allowed_border
+            keep = ((all_anchors[:, 0] >= -b) & (all_anchors[:, 1] >= -b) &
+                    (all_anchors[:, 2] < lim_w + b) & (all_anchors[:, 3] < lim_h + b))
+            inds = np.nonzero(keep)[0]
+            inv = np.full((all_anchors.shape[0],), -1, np.int32)
+            inv[inds] = np.arange(inds.shape[0], dtype=np.int32)
+            hit = (torch.from_numpy(np.ascontiguousarray(all_anchors[inds])).to(device),
+                   torch.from_numpy(inds).to(device), torch.from_numpy(inv).to(device))
+            if len(self._cache) > 16:
+                self._cache.clear()
+            self._cache[key] = hit
+        return hit
+
+    def forward(self, input):
+        rpn_cls_score, gt_boxes, im_info, num_boxes = input[0], input[1], input[2], input[3]
+        height, width = rpn_cls_score.size(2), rpn_cls_score.size(3)
+        batch_size = gt_boxes.size(0)
+        A = self._num_anchors
+        # :86-87 -- the FIRST image's size, truncated to int, is used for the whole batch
+        info0 = im_info[0].tolist()
+        anchors, inds_inside, inv_index = self._inside(height, width, int(info0[1]), int(info0[0]),
+                                                       gt_boxes.device)
+
+        labels, argmax = F.anchor_labels(anchors, gt_boxes, cfg.TRAIN.RPN_NEGATIVE_OVERLAP,
+                                         cfg.TRAIN.RPN_POSITIVE_OVERLAP, cfg.TRAIN.RPN_CLOBBER_POSITIVES)
+
+        # ---- host-side subsampling, :118-145 (same tensor ops, same RNG calls) ----
+        num_fg = int(cfg.TRAIN.RPN_FG_FRACTION * cfg.TRAIN.RPN_BATCHSIZE)
+        counts = torch.stack([torch.sum((labels == 1).int(), 1), torch.sum((labels == 0).int(), 1)]).tolist()
+        sum_fg, sum_bg = counts[0], counts[1]
+        i = 0
+        for i in range(batch_size):
+            if sum_fg[i] > num_fg:
+                fg_inds = torch.nonzero(labels[i] == 1).view(-1)
+                rand_num = torch.from_numpy(np.random.permutation(fg_inds.size(0))).to(fg_inds.device).long()
+                disable_inds = fg_inds[rand_num[:fg_inds.size(0) - num_fg]]
+                labels[i][disable_inds] = -1
+                n_fg_i = num_fg
+            else:
+                n_fg_i = sum_fg[i]
+            num_bg = cfg.TRAIN.RPN_BATCHSIZE - n_fg_i
+            if sum_bg[i] > num_bg:
+                bg_inds = torch.nonzero(labels[i] == 0).view(-1)
+                rand_num = torch.from_numpy(np.random.permutation(bg_inds.size(0))).to(bg_inds.device).long()
+                disable_inds = bg_inds[rand_num[:bg_inds.size(0) - num_bg]]
+                labels[i][disable_inds] = -1
+
+        inside_w = cfg.TRAIN.RPN_BBOX_INSIDE_WEIGHTS[0]
+        if cfg.TRAIN.RPN_POSITIVE_WEIGHT < 0:
+            # :155-158 -- num_examples of the LAST image (stale loop variable) for every image
+            num_examples = int(torch.sum(labels[i] >= 0).item())
+            positive_weights = 1.0 / num_examples if num_examples > 0 else float('inf')
+            negative_weights = positive_weights
+        else:
+            assert ((cfg.TRAIN.RPN_POSITIVE_WEIGHT > 0) & (cfg.TRAIN.RPN_POSITIVE_WEIGHT < 1))
+            raise NotImplementedError("RPN_POSITIVE_WEIGHT >= 0 leaves the weights undefined in the "
+                                      "reference as well (anchor_target_layer.py:159-164)")
+
+        labels_out, targets, inside, outside = F.anchor_targets_finalize(
+            labels, argmax, anchors, gt_boxes, inv_index, A, height, width, inside_w, positive_weights,
+            negative_weights)
+        return [labels_out, targets, inside, outside]
+
+    def backward(self, top, propagate_down, bottom):
+        """This layer does not propagate gradients."""
+        pass
+
+    def reshape(self, bottom, top):
+        pass

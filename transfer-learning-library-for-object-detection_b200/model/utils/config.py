@@ -1,0 +1,54 @@
+"""The subset of the reference's global ``cfg`` the hot path reads
+(lib/model/utils/config.py:11-305; keys listed in SURVEY.md section 5), with the
+reference's defaults.  The layers read this object at CALL time, never cache it
+(lib/ATF/faster_rcnn.py:260 mutates TEST.RPN_POST_NMS_TOP_N at run time).
+
+When this package is dropped into the reference tree, the reference's own
+``model/utils/config.py`` takes this file's place unchanged.
+"""
+
+
+class AttrDict(dict):
+    """easydict-style attribute access (easydict itself is not a dependency)."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+__C = AttrDict()
+cfg = __C
+
+__C.TRAIN = AttrDict()
+__C.TRAIN.RPN_POSITIVE_OVERLAP = 0.7      # config.py:131
+__C.TRAIN.RPN_NEGATIVE_OVERLAP = 0.3      # :134
+__C.TRAIN.RPN_CLOBBER_POSITIVES = False   # :136
+__C.TRAIN.RPN_FG_FRACTION = 0.5           # :138
+__C.TRAIN.RPN_BATCHSIZE = 256             # :140
+__C.TRAIN.RPN_NMS_THRESH = 0.7            # :142
+__C.TRAIN.RPN_PRE_NMS_TOP_N = 12000       # :144
+__C.TRAIN.RPN_POST_NMS_TOP_N = 2000       # :146
+__C.TRAIN.RPN_MIN_SIZE = 8                # :148 (read, unused: proposal_layer.py:75,113)
+__C.TRAIN.RPN_BBOX_INSIDE_WEIGHTS = (1.0, 1.0, 1.0, 1.0)  # :150
+__C.TRAIN.RPN_POSITIVE_WEIGHT = -1.0      # :154
+
+__C.TEST = AttrDict()
+__C.TEST.NMS = 0.3
+__C.TEST.RPN_NMS_THRESH = 0.7             # :193
+__C.TEST.RPN_PRE_NMS_TOP_N = 6000         # :195
+__C.TEST.RPN_POST_NMS_TOP_N = 300         # :198
+__C.TEST.RPN_MIN_SIZE = 16                # :201
+
+__C.RNG_SEED = 3                          # :262
+__C.USE_GPU_NMS = True                    # :281
+__C.POOLING_MODE = 'align'
+__C.POOLING_SIZE = 7                      # :289
+__C.MAX_NUM_GT_BOXES = 20                 # :292
+__C.ANCHOR_SCALES = [4, 8, 16, 32]        # :295 (scripts force this for cityscape)
+__C.ANCHOR_RATIOS = [0.5, 1, 2]           # :298
+__C.FEAT_STRIDE = [16, ]                  # :301

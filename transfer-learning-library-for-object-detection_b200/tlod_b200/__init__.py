@@ -1,0 +1,16 @@
+"""tlod_b200 -- B200-native (sm_100a) RoI / proposal hot path of
+live-group/Transfer-Learning-Library-for-Object-Detection.
+
+Host side of the C ABI in include/tlod_b200.h.  The reference-facing operator
+surface (``model.roi_align.modules.roi_align.RoIAlignAvg`` ...) lives in the
+sibling ``model`` package; put this directory on ``sys.path`` the way the
+reference's ``_init_paths.py`` adds ``lib/``.
+"""
+from . import _lib  # noqa: F401  (raises if libtlod_b200.so is missing)
+from . import functional  # noqa: F401
+from .autograd import (DALossFunction, GradReverse, RoIAlignFunction, RoIPoolFunction, da_losses,  # noqa: F401
+                       grad_reverse)
+from ._lib import TlodError, launch_count  # noqa: F401
+
+__all__ = ["functional", "RoIAlignFunction", "RoIPoolFunction", "GradReverse", "grad_reverse", "DALossFunction",
+           "da_losses", "TlodError", "launch_count"]

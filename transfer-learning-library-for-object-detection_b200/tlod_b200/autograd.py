@@ -1,0 +1,94 @@
+"""Autograd bindings (modern static Functions; the reference's are torch-0.4 instance
+Functions: lib/model/roi_align/functions/roi_align.py:8-51,
+lib/model/roi_pooling/functions/roi_pool.py:6-38, lib/DAF/DA.py:19-33)."""
+from __future__ import annotations
+
+import torch
+from torch.autograd import Function
+
+from . import functional as F
+
+
+class RoIAlignFunction(Function):
+    """features (B,C,H,W), rois (R,5) -> (R,C,aligned_h,aligned_w); grad only w.r.t. features."""
+
+    @staticmethod
+    def forward(ctx, features, rois, aligned_height, aligned_width, spatial_scale):
+        ctx.save_for_backward(rois)
+        ctx.feature_size = tuple(features.shape)
+        ctx.scale = float(spatial_scale)
+        return F.roi_align_forward(features, rois, int(aligned_height), int(aligned_width), ctx.scale)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        (rois,) = ctx.saved_tensors
+        assert grad_output.is_cuda  # functions/roi_align.py:38
+        grad_input = F.roi_align_backward(grad_output, rois, ctx.feature_size, ctx.scale)
+        return grad_input, None, None, None, None
+
+
+class RoIPoolFunction(Function):
+    @staticmethod
+    def forward(ctx, features, rois, pooled_height, pooled_width, spatial_scale):
+        out, argmax = F.roi_pool_forward(features, rois, int(pooled_height), int(pooled_width),
+                                         float(spatial_scale))
+        ctx.save_for_backward(rois, argmax)
+        ctx.feature_size = tuple(features.shape)
+        ctx.scale = float(spatial_scale)
+        ctx.mark_non_differentiable(argmax)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        rois, argmax = ctx.saved_tensors
+        assert grad_output.is_cuda
+        grad_input = F.roi_pool_backward(grad_output, argmax, rois, ctx.feature_size, ctx.scale)
+        return grad_input, None, None, None, None
+
+
+class GradReverse(Function):
+    """Identity forward; backward -alpha * g (optionally * per-row weight, lib/MAF/DA.py:34-53)."""
+
+    @staticmethod
+    def forward(ctx, x, alpha=0.1, row_weight=None):
+        ctx.alpha = float(alpha)
+        ctx.has_w = row_weight is not None
+        if ctx.has_w:
+            ctx.save_for_backward(row_weight)
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        w = ctx.saved_tensors[0] if ctx.has_w else None
+        return F.grl_backward(grad_output, ctx.alpha, w), None, None
+
+
+def grad_reverse(x, alpha=0.1, row_weight=None):
+    return GradReverse.apply(x, alpha, row_weight)
+
+
+class DALossFunction(Function):
+    """(img_score (B,2,H,W), ins_prob (R,1)) -> (img_loss, ins_loss, cst_loss) for one domain,
+    lib/DAF/faster_rcnn.py:181-220.  One launch forward, one backward, no label tensors."""
+
+    @staticmethod
+    def forward(ctx, img_score, ins_prob, domain_label, ins_label=None):
+        losses = F.da_loss_forward(img_score, ins_prob, int(domain_label), ins_label)
+        ctx.save_for_backward(img_score, ins_prob, losses, *([] if ins_label is None else [ins_label]))
+        ctx.domain = int(domain_label)
+        ctx.has_label = ins_label is not None
+        return losses[0], losses[1], losses[2]
+
+    @staticmethod
+    def backward(ctx, g_img, g_ins, g_cst):
+        saved = ctx.saved_tensors
+        img_score, ins_prob, losses = saved[:3]
+        lab = saved[3] if ctx.has_label else None
+        # the three upstream gradients stay on the device (no .item() sync)
+        up = torch.stack([g_img.reshape(()), g_ins.reshape(()), g_cst.reshape(())]).float()
+        gi, gp = F.da_loss_backward(img_score, ins_prob, ctx.domain, losses, 1.0, 1.0, 1.0, lab, upstream=up)
+        return gi, gp.view_as(ins_prob), None, None
+
+
+def da_losses(img_score, ins_prob, domain_label, ins_label=None):
+    return DALossFunction.apply(img_score, ins_prob, domain_label, ins_label)

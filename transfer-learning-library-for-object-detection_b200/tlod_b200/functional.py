@@ -1,0 +1,329 @@
+"""Torch-facing wrappers over the C ABI (PyTorch is plumbing: device memory and streams).
+
+Every function takes CUDA fp32 tensors, allocates outputs / workspaces with torch
+on the tensors' device, and enqueues the kernels on torch's current stream.  None of
+them synchronises the host.  A CPU tensor is an error -- there is no CPU path.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import check, lib
+
+_workspaces = {}
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("tlod_b200 has no CPU implementation: got a %s tensor" % t.device)
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _workspace(device, nbytes: int, tag: str) -> torch.Tensor:
+    """Grow-only scratch buffer per (device, stream, tag)."""
+    key = (device.index, _stream(device), tag)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+# ---------------------------------------------------------------------------
+# RoIAlign / RoIPool
+# ---------------------------------------------------------------------------
+def roi_align_forward(features, rois, aligned_h: int, aligned_w: int, spatial_scale: float):
+    _require_cuda(features, rois)
+    features, rois = _f32(features), _f32(rois)
+    if rois.dim() != 2 or rois.size(1) != 5:
+        raise ValueError("rois must be (R, 5) [batch_idx, x1, y1, x2, y2]")
+    B, C, H, W = features.shape
+    R = rois.size(0)
+    out = torch.empty((R, C, aligned_h, aligned_w), dtype=torch.float32, device=features.device)
+    with torch.cuda.device(features.device):
+        check(lib.tlod_roi_align_forward(features.data_ptr(), rois.data_ptr(), out.data_ptr(), B, C, H, W, R,
+                                         int(aligned_h), int(aligned_w), float(spatial_scale),
+                                         _stream(features.device)), "tlod_roi_align_forward")
+    return out
+
+
+def roi_align_backward(top_grad, rois, feature_size, spatial_scale: float):
+    _require_cuda(top_grad, rois)
+    top_grad, rois = _f32(top_grad), _f32(rois)
+    B, C, H, W = [int(v) for v in feature_size]
+    R, _, AH, AW = top_grad.shape
+    grad = torch.empty((B, C, H, W), dtype=torch.float32, device=top_grad.device)
+    with torch.cuda.device(top_grad.device):
+        check(lib.tlod_roi_align_backward(top_grad.data_ptr(), rois.data_ptr(), grad.data_ptr(), B, C, H, W, R,
+                                          AH, AW, float(spatial_scale), _stream(top_grad.device)),
+              "tlod_roi_align_backward")
+    return grad
+
+
+def roi_pool_forward(features, rois, pooled_h: int, pooled_w: int, spatial_scale: float):
+    _require_cuda(features, rois)
+    features, rois = _f32(features), _f32(rois)
+    if rois.dim() != 2 or rois.size(1) != 5:
+        raise ValueError("rois must be (R, 5) [batch_idx, x1, y1, x2, y2]")
+    B, C, H, W = features.shape
+    R = rois.size(0)
+    out = torch.empty((R, C, pooled_h, pooled_w), dtype=torch.float32, device=features.device)
+    argmax = torch.empty((R, C, pooled_h, pooled_w), dtype=torch.int32, device=features.device)
+    with torch.cuda.device(features.device):
+        check(lib.tlod_roi_pool_forward(features.data_ptr(), rois.data_ptr(), out.data_ptr(), argmax.data_ptr(),
+                                        B, C, H, W, R, int(pooled_h), int(pooled_w), float(spatial_scale),
+                                        _stream(features.device)), "tlod_roi_pool_forward")
+    return out, argmax
+
+
+def roi_pool_backward(top_grad, argmax, rois, feature_size, spatial_scale: float):
+    _require_cuda(top_grad, argmax, rois)
+    top_grad, rois = _f32(top_grad), _f32(rois)
+    argmax = argmax.contiguous()
+    B, C, H, W = [int(v) for v in feature_size]
+    R, _, PH, PW = top_grad.shape
+    grad = torch.empty((B, C, H, W), dtype=torch.float32, device=top_grad.device)
+    with torch.cuda.device(top_grad.device):
+        check(lib.tlod_roi_pool_backward(top_grad.data_ptr(), argmax.data_ptr(), rois.data_ptr(), grad.data_ptr(),
+                                         B, C, H, W, R, PH, PW, float(spatial_scale), _stream(top_grad.device)),
+              "tlod_roi_pool_backward")
+    return grad
+
+
+# ---------------------------------------------------------------------------
+# NMS / proposals
+# ---------------------------------------------------------------------------
+def nms_device(dets, thresh: float, max_keep: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """dets (n, >=4) sorted by score -> (keep int32 (n,), num int32 (1,)), both on the
+    device, no host synchronisation (keep[num:] is unspecified)."""
+    _require_cuda(dets)
+    dets = _f32(dets)
+    n, stride = dets.shape
+    keep = torch.empty((max(n, 1),), dtype=torch.int32, device=dets.device)
+    num = torch.zeros((1,), dtype=torch.int32, device=dets.device)
+    if n == 0:
+        return keep[:0], num
+    nbytes = lib.tlod_nms_workspace_bytes(n)
+    ws = _workspace(dets.device, nbytes, "nms")
+    with torch.cuda.device(dets.device):
+        check(lib.tlod_nms(dets.data_ptr(), n, stride, float(thresh), int(max_keep), keep.data_ptr(),
+                           num.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dets.device)), "tlod_nms")
+    return keep, num
+
+
+def proposals(scores, deltas, im_info, anchors, feat_stride: int, pre_nms_topN: int, post_nms_topN: int,
+              nms_thresh: float, return_debug: bool = False):
+    """Fused batched proposal layer -> rois (B, post_nms_topN, 5)."""
+    _require_cuda(scores, deltas, im_info, anchors)
+    scores, deltas, im_info, anchors = _f32(scores), _f32(deltas), _f32(im_info), _f32(anchors)
+    B, A2, H, W = scores.shape
+    A = A2 // 2
+    if anchors.shape != (A, 4) or deltas.shape != (B, 4 * A, H, W) or im_info.shape[0] != B:
+        raise ValueError("inconsistent proposal-layer shapes")
+    dev = scores.device
+    rois = torch.empty((B, post_nms_topN, 5), dtype=torch.float32, device=dev)
+    n_sorted = lib.tlod_proposals_n_sorted(B, A, H, W, int(pre_nms_topN))
+    order = boxes = num = None
+    if return_debug:
+        order = torch.empty((B, n_sorted), dtype=torch.int32, device=dev)
+        boxes = torch.empty((B, n_sorted, 4), dtype=torch.float32, device=dev)
+        num = torch.empty((B,), dtype=torch.int32, device=dev)
+    nbytes = lib.tlod_proposals_workspace_bytes(B, A, H, W, int(pre_nms_topN), int(post_nms_topN))
+    ws = _workspace(dev, nbytes, "proposals")
+    with torch.cuda.device(dev):
+        check(lib.tlod_proposals(scores.data_ptr(), deltas.data_ptr(), im_info.data_ptr(), anchors.data_ptr(),
+                                 rois.data_ptr(), B, A, H, W, int(feat_stride), int(pre_nms_topN),
+                                 int(post_nms_topN), float(nms_thresh), _ptr(order), _ptr(boxes), _ptr(num),
+                                 ws.data_ptr(), ws.numel(), _stream(dev)), "tlod_proposals")
+    if return_debug:
+        return rois, order, boxes, num
+    return rois
+
+
+# ---------------------------------------------------------------------------
+# box arithmetic
+# ---------------------------------------------------------------------------
+def bbox_transform_inv(boxes, deltas, im_info=None):
+    """boxes (B,N,4) or (N,4); deltas (B,N,4) -> (B,N,4), clipped if im_info given."""
+    _require_cuda(boxes, deltas, im_info)
+    boxes, deltas = _f32(boxes), _f32(deltas)
+    B, N, _ = deltas.shape
+    batched = 1 if boxes.dim() == 3 else 0
+    out = torch.empty_like(deltas)
+    info = None if im_info is None else _f32(im_info)
+    with torch.cuda.device(deltas.device):
+        check(lib.tlod_bbox_transform_inv_clip(boxes.data_ptr(), batched, deltas.data_ptr(), _ptr(info),
+                                               out.data_ptr(), B, N, _stream(deltas.device)),
+              "tlod_bbox_transform_inv_clip")
+    return out
+
+
+def clip_boxes_(boxes, im_info):
+    """In place; boxes (B, N, 4k) contiguous fp32."""
+    _require_cuda(boxes, im_info)
+    if boxes.dtype != torch.float32 or not boxes.is_contiguous():
+        raise ValueError("clip_boxes_ needs a contiguous fp32 tensor")
+    B, N, K4 = boxes.shape
+    info = _f32(im_info)
+    with torch.cuda.device(boxes.device):
+        check(lib.tlod_clip_boxes(boxes.data_ptr(), info.data_ptr(), B, N, K4 // 4, _stream(boxes.device)),
+              "tlod_clip_boxes")
+    return boxes
+
+
+def bbox_overlaps_batch(anchors, gt_boxes):
+    """anchors (N,4) | (B,N,4) | (B,N,5: batch idx first); gt (B,K,>=4) -> (B,N,K)."""
+    _require_cuda(anchors, gt_boxes)
+    anchors, gt = _f32(anchors), _f32(gt_boxes)
+    B, K, gs = gt.shape
+    if anchors.dim() == 2:
+        batched, N, stride, off = 0, anchors.size(0), anchors.size(1), 0
+    elif anchors.dim() == 3:
+        batched, N, stride = 1, anchors.size(1), anchors.size(2)
+        off = 0 if stride == 4 else 1
+    else:
+        raise ValueError("anchors input dimension is not correct.")
+    out = torch.empty((B, N, K), dtype=torch.float32, device=gt.device)
+    with torch.cuda.device(gt.device):
+        check(lib.tlod_bbox_overlaps_batch(anchors.data_ptr(), batched, stride, off, gt.data_ptr(), gs,
+                                           out.data_ptr(), B, N, K, _stream(gt.device)),
+              "tlod_bbox_overlaps_batch")
+    return out
+
+
+def bbox_transform_batch(ex_rois, gt_rois):
+    _require_cuda(ex_rois, gt_rois)
+    ex, gt = _f32(ex_rois), _f32(gt_rois)
+    B, N, _ = gt.shape
+    batched = 1 if ex.dim() == 3 else 0
+    out = torch.empty((B, N, 4), dtype=torch.float32, device=gt.device)
+    with torch.cuda.device(gt.device):
+        check(lib.tlod_bbox_transform_batch(ex.data_ptr(), batched, gt.data_ptr(), out.data_ptr(), B, N,
+                                            _stream(gt.device)), "tlod_bbox_transform_batch")
+    return out
+
+
+# ---------------------------------------------------------------------------
+# anchor targets
+# ---------------------------------------------------------------------------
+def anchor_labels(anchors, gt_boxes, negative_overlap: float, positive_overlap: float,
+                  clobber_positives: bool = False, want_max: bool = False):
+    _require_cuda(anchors, gt_boxes)
+    anchors, gt = _f32(anchors), _f32(gt_boxes)
+    B, K, gs = gt.shape
+    N = anchors.size(0)
+    dev = gt.device
+    labels = torch.empty((B, N), dtype=torch.float32, device=dev)
+    argmax = torch.empty((B, N), dtype=torch.int32, device=dev)
+    mx = torch.empty((B, N), dtype=torch.float32, device=dev) if want_max else None
+    ws = _workspace(dev, lib.tlod_anchor_labels_workspace_bytes(B, K), "anchor_labels")
+    with torch.cuda.device(dev):
+        check(lib.tlod_anchor_labels(anchors.data_ptr(), gt.data_ptr(), gs, labels.data_ptr(), argmax.data_ptr(),
+                                     _ptr(mx), B, N, K, float(negative_overlap), float(positive_overlap),
+                                     int(bool(clobber_positives)), ws.data_ptr(), ws.numel(), _stream(dev)),
+              "tlod_anchor_labels")
+    return (labels, argmax, mx) if want_max else (labels, argmax)
+
+
+def anchor_targets_finalize(labels, argmax, anchors, gt_boxes, inv_index, num_anchors: int, height: int,
+                            width: int, inside_weight: float, positive_weight: float, negative_weight: float):
+    _require_cuda(labels, argmax, anchors, gt_boxes, inv_index)
+    labels, anchors, gt = _f32(labels), _f32(anchors), _f32(gt_boxes)
+    argmax = argmax.contiguous()
+    inv_index = inv_index.contiguous()
+    B, N = labels.shape
+    K, gs = gt.size(1), gt.size(2)
+    A, H, W = int(num_anchors), int(height), int(width)
+    dev = labels.device
+    labels_out = torch.empty((B, 1, A * H, W), dtype=torch.float32, device=dev)
+    targets = torch.empty((B, 4 * A, H, W), dtype=torch.float32, device=dev)
+    inside = torch.empty_like(targets)
+    outside = torch.empty_like(targets)
+    with torch.cuda.device(dev):
+        check(lib.tlod_anchor_targets_finalize(labels.data_ptr(), argmax.data_ptr(), anchors.data_ptr(),
+                                               gt.data_ptr(), gs, inv_index.data_ptr(), labels_out.data_ptr(),
+                                               targets.data_ptr(), inside.data_ptr(), outside.data_ptr(), B, N, K,
+                                               A, H, W, float(inside_weight), float(positive_weight),
+                                               float(negative_weight), _stream(dev)),
+              "tlod_anchor_targets_finalize")
+    return labels_out, targets, inside, outside
+
+
+# ---------------------------------------------------------------------------
+# GRL + DA losses
+# ---------------------------------------------------------------------------
+def grl_backward(grad, alpha: float, row_weight=None):
+    _require_cuda(grad, row_weight)
+    grad = _f32(grad)
+    out = torch.empty_like(grad)
+    with torch.cuda.device(grad.device):
+        if row_weight is None:
+            check(lib.tlod_grl_backward(grad.data_ptr(), out.data_ptr(), float(alpha), grad.numel(),
+                                        _stream(grad.device)), "tlod_grl_backward")
+        else:
+            w = _f32(row_weight).view(-1)
+            rows = grad.size(0)
+            cols = grad.numel() // max(rows, 1)
+            if w.numel() != rows:
+                raise ValueError("row_weight must have one entry per row")
+            check(lib.tlod_grl_backward_weighted(grad.data_ptr(), w.data_ptr(), out.data_ptr(), float(alpha), rows,
+                                                 cols, _stream(grad.device)), "tlod_grl_backward_weighted")
+    return out
+
+
+def da_loss_forward(img_score, ins_prob, domain_label: int, ins_label=None):
+    """-> losses (4,) device tensor [img_nll_mean, ins_bce_mean, cst_mse_sum, consistency_target]."""
+    _require_cuda(img_score, ins_prob, ins_label)
+    img_score, ins_prob = _f32(img_score), _f32(ins_prob).view(-1)
+    B, two, H, W = img_score.shape
+    if two != 2:
+        raise ValueError("img_score must be (B, 2, H, W)")
+    lab = None if ins_label is None else _f32(ins_label).view(-1)
+    dev = img_score.device
+    out = torch.empty((4,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.tlod_da_loss_forward(img_score.data_ptr(), ins_prob.data_ptr(), _ptr(lab), int(domain_label),
+                                       out.data_ptr(), B, H, W, ins_prob.numel(), None, 0, _stream(dev)),
+              "tlod_da_loss_forward")
+    return out
+
+
+def da_loss_backward(img_score, ins_prob, domain_label: int, losses, w_img: float, w_ins: float, w_cst: float,
+                     ins_label=None, upstream=None):
+    """upstream: optional (3,) device tensor multiplied into (w_img, w_ins, w_cst) on the device."""
+    _require_cuda(img_score, ins_prob, losses, ins_label, upstream)
+    up = None if upstream is None else _f32(upstream)
+    img_score, ins_prob = _f32(img_score), _f32(ins_prob)
+    B, _, H, W = img_score.shape
+    lab = None if ins_label is None else _f32(ins_label).view(-1)
+    g_img = torch.empty_like(img_score)
+    g_ins = torch.empty_like(ins_prob)
+    dev = img_score.device
+    with torch.cuda.device(dev):
+        check(lib.tlod_da_loss_backward(img_score.data_ptr(), ins_prob.data_ptr(), _ptr(lab), int(domain_label),
+                                        losses.data_ptr(), _ptr(up), float(w_img), float(w_ins), float(w_cst),
+                                        g_img.data_ptr(), g_ins.data_ptr(), B, H, W, ins_prob.numel(),
+                                        _stream(dev)), "tlod_da_loss_backward")
+    return g_img, g_ins
+
+
+launch_count = _lib.launch_count
