@@ -1,0 +1,430 @@
+#!/usr/bin/env python
+"""Benchmark of the RoI / proposal hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # reference CPU path (oracle port)
+
+Workload (BASELINE.json configs[1]), per GPU: one DAF-style
+training step's operator sequence on 2 source + 2 target synthetic 600x1200 images
+(VGG16 conv5 maps 512x37x75, A = 12 anchors):
+  source: proposal layer TRAIN (12000 -> 2000, NMS 0.7), anchor targets, RoIAlignAvg 7x7
+          forward + backward on 256 RoIs/image, image/instance DA losses fwd+bwd, GRL;
+  target: proposal layer TEST (6000 -> 300), RoIAlignAvg forward + backward on 300
+          RoIs/image, DA losses fwd+bwd, GRL.
+`value` = RoIs pooled forward+backward per second over the whole step, all GPUs
+(weak scaling: every rank runs its own 4 images; there is no collective on the path).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "transfer-learning-library-for-object-detection_b200")
+for p in (PKG, ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+C, H, W, A = 512, 37, 75, 12
+N_SRC, N_TGT = 2, 2
+ROIS_SRC, ROIS_TGT = 256, 300
+ROIS_PER_STEP = N_SRC * ROIS_SRC + N_TGT * ROIS_TGT
+PROPOSALS_PER_STEP = N_SRC * 2000 + N_TGT * 300
+WORKLOAD = ("cfg2: DAF VGG16 step ops, 2 src + 2 tgt 600x1200 images/GPU, conv5 512x37x75, "
+            "RPN 12000->2000 (src) / 6000->300 (tgt) NMS 0.7, RoIAlignAvg 7x7 fwd+bwd on 256/300 RoIs per image, "
+            "anchor targets, image+instance DA losses, GRL")
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def synth_inputs(seed, pin=False):
+    """Host tensors of one rank's step (SURVEY.md 8d generators)."""
+    from oracle.synth import synth_gt, synth_rpn
+    g = torch.Generator().manual_seed(seed)
+    d = {}
+    for dom, n in (("src", N_SRC), ("tgt", N_TGT)):
+        d[dom + "_feat"] = torch.relu(torch.randn(n, C, H, W, generator=g))
+        prob, deltas = synth_rpn(n, A, H, W, seed + (1 if dom == "src" else 2))
+        d[dom + "_prob"], d[dom + "_deltas"] = prob, deltas
+        d[dom + "_im_info"] = torch.tensor([[600.0, 1200.0, 0.5859375]] * n)
+        d[dom + "_img_score"] = torch.randn(n, 2, H, W, generator=g)
+        r = n * (ROIS_SRC if dom == "src" else ROIS_TGT)
+        d[dom + "_ins_prob"] = torch.sigmoid(torch.randn(r, 1, generator=g))
+    d["src_gt"] = synth_gt(N_SRC, 20, 50, seed + 50)
+    if pin:
+        d = {k: v.pin_memory() for k, v in d.items()}
+    return d
+
+
+# ---------------------------------------------------------------------------
+# this repo's arm
+# ---------------------------------------------------------------------------
+class TlodStep(object):
+    def __init__(self, dev, seed):
+        from model.roi_align.modules.roi_align import RoIAlignAvg
+        from model.rpn.anchor_target_layer import _AnchorTargetLayer
+        from model.rpn.proposal_layer import _ProposalLayer
+        import tlod_b200
+        self.tlod = tlod_b200
+        self.dev = dev
+        self.host = synth_inputs(seed, pin=True)
+        self.d = {k: v.to(dev) for k, v in self.host.items()}
+        self.proposal = _ProposalLayer(16, [4, 8, 16, 32], [0.5, 1, 2])
+        self.anchor_target = _AnchorTargetLayer(16, [4, 8, 16, 32], [0.5, 1, 2])
+        self.roi_align = RoIAlignAvg(7, 7, 1.0 / 16.0)
+        g = torch.Generator().manual_seed(seed + 99)
+        # gradient arriving from the detection head: device resident (it never exists on the host)
+        self.top = {"src": torch.randn(N_SRC * ROIS_SRC, C, 7, 7, generator=g).to(dev),
+                    "tgt": torch.randn(N_TGT * ROIS_TGT, C, 7, 7, generator=g).to(dev)}
+        self.num_boxes = torch.full((N_SRC,), 20, dtype=torch.long)
+        np.random.seed(3)
+
+    def domain(self, dom, d, results):
+        key = "TRAIN" if dom == "src" else "TEST"
+        per = ROIS_SRC if dom == "src" else ROIS_TGT
+        feat = d[dom + "_feat"].requires_grad_(True)
+        rois = self.proposal((d[dom + "_prob"], d[dom + "_deltas"], d[dom + "_im_info"], key))
+        if dom == "src":
+            results["anchor_targets"] = self.anchor_target((d["src_prob"], d["src_gt"], d["src_im_info"],
+                                                            self.num_boxes))
+        sel = rois[:, :per, :].reshape(-1, 5)  # stand-in for _ProposalTargetLayer's sampling
+        pooled = self.roi_align(feat, sel)
+        score = d[dom + "_img_score"].requires_grad_(True)
+        prob = d[dom + "_ins_prob"].requires_grad_(True)
+        img, ins, cst = self.tlod.da_losses(score, prob, 1 if dom == "src" else 0)
+        loss = 0.1 * (img + ins + cst)
+        torch.autograd.backward([pooled, loss], [self.top[dom], None])
+        # GRL in front of the DA heads: base_feat gradient and pooled-feature gradient
+        g_feat = self.tlod.functional.grl_backward(feat.grad, 0.1)
+        results[dom] = (rois, feat.grad, g_feat, torch.stack([img, ins, cst]).detach(), score.grad, prob.grad)
+        feat.grad = None
+
+    def step(self, d=None):
+        d = self.d if d is None else d
+        results = {}
+        self.domain("src", d, results)
+        self.domain("tgt", d, results)
+        return results
+
+    def step_e2e(self):
+        """Same step through host buffers: H2D of the inputs from pinned memory, D2H of the results."""
+        d = {k: v.to(self.dev, non_blocking=True) for k, v in self.host.items()}
+        r = self.step(d)
+        out = []
+        for dom in ("src", "tgt"):
+            rois, gfeat, _, losses, _, _ = r[dom]
+            out += [rois.cpu(), gfeat.cpu(), losses.cpu()]
+        out.append(r["anchor_targets"][0].cpu())
+        return out
+
+    def e2e_bytes(self):
+        h2d = sum(v.numel() * v.element_size() for v in self.host.values())
+        d2h = 0
+        for dom, n, per in (("src", N_SRC, 2000), ("tgt", N_TGT, 300)):
+            d2h += n * per * 5 * 4 + n * C * H * W * 4 + 3 * 4
+        d2h += N_SRC * A * H * W * 4
+        return h2d, d2h
+
+
+def clocks_sampler(path):
+    q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    try:
+        return subprocess.Popen(["nvidia-smi", "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100",
+                                 "-i", "0"], stdout=open(path, "w"), stderr=subprocess.DEVNULL)
+    except Exception:
+        return None
+
+
+def parse_clocks(path):
+    sm, mx, reasons = [], [], set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    try:
+        for line in open(path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            sm.append(float(f[1]))
+            mx.append(float(f[2]))
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+    except Exception:
+        pass
+    if not sm:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+    return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons)}
+
+
+def roi_align_cfg3(dev, iters=20):
+    """RoIAlign 8x8 forward and backward at BASELINE cfg3 (ResNet-101 conv4, batch 8, 256 RoIs/image)."""
+    from oracle.synth import synth_rois
+    from tlod_b200 import functional as F
+    peak, peak_src = peaks()
+    B, Cc, Hh, Ww, R = 8, 1024, 38, 75, 2048
+    g = torch.Generator().manual_seed(7)
+    x = torch.relu(torch.randn(B, Cc, Hh, Ww, generator=g)).to(dev)
+    rois = synth_rois(R, B, 41).to(dev)
+    rois = rois[torch.argsort(rois[:, 0], stable=True)].contiguous()  # (B, 256, 5).view(-1, 5) order
+    top = torch.randn(R, Cc, 8, 8, device=dev)
+    alg = B * Cc * Hh * Ww * 4 + R * 20 + R * Cc * 64 * 4
+    out = {}
+    for name, fn in (("fwd", lambda: F.roi_align_forward(x, rois, 8, 8, 1.0 / 16)),
+                     ("bwd", lambda: F.roi_align_backward(top, rois, x.shape, 1.0 / 16))):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / iters
+        out[name] = {"ms": ms, "achieved_GBps": alg / ms / 1e6, "frac_of_hbm_peak": alg / ms / 1e6 / peak}
+    out["algorithmic_bytes_per_direction"] = alg
+    out["rois_per_s_fwd_bwd"] = R / ((out["fwd"]["ms"] + out["bwd"]["ms"]) * 1e-3)
+    out["frac_fwd_bwd"] = 2 * alg / ((out["fwd"]["ms"] + out["bwd"]["ms"]) * 1e6) / peak
+    out["peak_GBps"] = peak
+    out["peak_source"] = peak_src
+    out["note"] = "includes the torch.empty allocation of the output inside each call (caching allocator)"
+    return out
+
+
+def run_tlod(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    import tlod_b200
+    from tlod_b200 import _lib
+
+    step = TlodStep(dev, seed=3 + rank)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        evs = []
+        wall0 = time.perf_counter()
+        for _ in range(steps):
+            flush.zero_()  # L2 flush between timed iterations, outside the event pair
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            evs.append((a, b))
+        barrier()
+        wall = time.perf_counter() - wall0
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, wall
+
+    clock_file = os.path.join(ROOT, "gpurun_out", "bench_clocks_rank0.csv")
+    os.makedirs(os.path.dirname(clock_file), exist_ok=True)
+    sampler = clocks_sampler(clock_file) if rank == 0 else None
+    launches0 = tlod_b200.launch_count()
+    ms_dev, wall = timed(step.step, args.steps, args.warmup)
+    launches = (tlod_b200.launch_count() - launches0) // (args.steps + args.warmup) * args.steps
+    ms_e2e, _ = timed(step.step_e2e, args.steps, max(3, args.warmup // 2))
+    if sampler is not None:
+        sampler.terminate()
+        sampler.wait()
+
+    # per-kernel device time (CUDA events on the launch stream, inside the library)
+    _lib.profile_reset()
+    _lib.profile(True)
+    for _ in range(max(5, min(args.steps, 20))):
+        flush.zero_()
+        step.step()
+    torch.cuda.synchronize()
+    prof = _lib.profile_read()
+    _lib.profile(False)
+
+    # HBM-bound evidence: RoIAlign forward / backward alone at cfg3 scale (8x1024x38x75, 2048 RoIs,
+    # 630 MB of algorithmic traffic per direction: larger than L2, so no flush is needed)
+    cfg3 = None
+    if rank == 0 and not args.no_cfg3:
+        cfg3 = roi_align_cfg3(dev)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = peaks()
+    total_ms = sum(v[0] for v in prof.values()) or 1.0
+    kernels = {k: {"ms_per_launch": v[0] / v[1], "launches": v[1], "share": v[0] / total_ms}
+               for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
+    # algorithmic bytes of the RoIAlign kernels at this workload: feature map once +
+    # rois + (R, C, 8, 8) tensor once; src and tgt launches alternate, so use the per-launch mean
+    def roi_bytes(n_img, n_roi):
+        return n_img * C * H * W * 4 + n_roi * 20 + n_roi * C * 64 * 4
+    mean_bytes = (roi_bytes(N_SRC, N_SRC * ROIS_SRC) + roi_bytes(N_TGT, N_TGT * ROIS_TGT)) / 2.0
+    dominant = next(iter(kernels)) if kernels else None
+    roof_kernel = "roi_align_fwd_planes_kernel"
+    roofline = None
+    if roof_kernel in kernels:
+        t = kernels[roof_kernel]["ms_per_launch"] * 1e-3
+        ach = mean_bytes / t / 1e9
+        roofline = {"kernel": roof_kernel, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": mean_bytes,
+                    "note": "working set fits L2 at this config; L2 flushed between steps"}
+    bwd_name = next((k for k in kernels if k.startswith("roi_align_bwd")), None)
+    roofline_bwd = None
+    if bwd_name:
+        t = kernels[bwd_name]["ms_per_launch"] * 1e-3
+        ach = mean_bytes / t / 1e9
+        roofline_bwd = {"kernel": bwd_name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                        "frac": ach / peak}
+    h2d, d2h = step.e2e_bytes()
+    line = {
+        "metric": "RoIs/sec RoIAlign fwd+bwd & proposals/sec (12000->2000 NMS) vs HBM roofline",
+        "value": world * ROIS_PER_STEP * args.steps / (ms_dev * 1e-3),
+        "unit": "RoIs/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rois_per_step_per_gpu": ROIS_PER_STEP,
+                   "proposals_per_step_per_gpu": PROPOSALS_PER_STEP, "images_per_step_per_gpu": N_SRC + N_TGT,
+                   "l2": "256 MB buffer zeroed between timed iterations (outside the event pairs)",
+                   "parallelism": "image-sharded, %d rank(s), no data-path collective" % world},
+        "proposals_per_s": world * PROPOSALS_PER_STEP * args.steps / (ms_dev * 1e-3),
+        "e2e": {"value": world * ROIS_PER_STEP * args.steps / (ms_e2e * 1e-3), "unit": "RoIs/s",
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": parse_clocks(clock_file),
+        "roofline": roofline, "roofline_roi_align_bwd": roofline_bwd,
+        "dominant_kernel": dominant, "kernels": kernels, "roi_align_cfg3": cfg3,
+        "wall_s": wall,
+    }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_reference(steps=2, warmup=0, threads=os.cpu_count())
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: the oracle (C restatement of the reference's kernels + numpy host logic)
+# ---------------------------------------------------------------------------
+def cpu_step(inp, anchors, orc, half):
+    """One (half) step on the CPU.  half=True: 1 source + 1 target image (bounded sample)."""
+    n_rois = 0
+    for dom, key, per, pre, post in (("src", "TRAIN", ROIS_SRC, 12000, 2000), ("tgt", "TEST", ROIS_TGT, 6000, 300)):
+        n = 1 if half else (N_SRC if dom == "src" else N_TGT)
+        feat = inp[dom + "_feat"][:n].numpy()
+        rois = orc.proposal_layer(inp[dom + "_prob"][:n].numpy(), inp[dom + "_deltas"][:n].numpy(),
+                                  inp[dom + "_im_info"][:n].numpy(), anchors, 16, pre, post, 0.7)
+        if dom == "src":
+            orc.anchor_target_layer(H, W, inp["src_gt"][:n].numpy(), inp["src_im_info"][:n].numpy(), anchors, 16)
+        sel = np.ascontiguousarray(rois[:, :per, :].reshape(-1, 5))
+        out8 = orc.roi_align_forward(feat, sel, 8, 8, 1.0 / 16)
+        pooled = torch.nn.functional.avg_pool2d(torch.from_numpy(out8), 2, 1)
+        top8 = np.ascontiguousarray(np.random.RandomState(0).randn(*out8.shape).astype(np.float32))
+        orc.roi_align_backward(top8, sel, feat.shape, 1.0 / 16)
+        r = sel.shape[0]
+        orc.da_losses(inp[dom + "_img_score"][:n].numpy(), inp[dom + "_ins_prob"][:r].numpy(), 1 if dom == "src" else 0)
+        orc.da_losses_grad(inp[dom + "_img_score"][:n].numpy(), inp[dom + "_ins_prob"][:r].numpy(),
+                           1 if dom == "src" else 0)
+        _ = pooled.sum()
+        n_rois += r
+    return n_rois
+
+
+def cpu_reference(steps, warmup, threads):
+    from oracle import oracle as orc
+    orc.build()
+    orc.set_num_threads(threads)
+    torch.set_num_threads(threads)
+    anchors = orc.generate_anchors(scales=[4, 8, 16, 32], ratios=[0.5, 1, 2]).astype(np.float32)
+    inp = synth_inputs(3)
+    np.random.seed(3)
+    for _ in range(warmup):
+        cpu_step(inp, anchors, orc, half=True)
+    t0 = time.perf_counter()
+    n = 0
+    for _ in range(steps):
+        n += cpu_step(inp, anchors, orc, half=True)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "RoIs/s", "cores": int(orc.num_threads()), "kind": "port",
+            "sample": "%d x half step (1 src + 1 tgt image, %d RoIs): oracle C port of the reference kernels "
+                      "(OpenMP over RoIs/images/channels) + numpy anchor targets; %.1f s" % (steps, n // max(steps, 1), dt),
+            "seconds": dt}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    steps, warmup = args.steps, min(args.warmup, 1)
+    # bounded: ~1-2 s per half step -> cap the number of timed steps so the run ends in minutes
+    steps_run = min(steps, 20)
+    base = cpu_reference(steps=steps_run, warmup=warmup, threads=os.cpu_count())
+    line = {
+        "impl": "reference",
+        "metric": "RoIs/sec RoIAlign fwd+bwd & proposals/sec (12000->2000 NMS) vs HBM roofline",
+        "value": base["value"], "unit": "RoIs/s", "n_gpus": world, "steps": steps_run, "warmup": warmup,
+        "ms_per_step": base["seconds"] / steps_run * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample_per_step": "half step: 1 src + 1 tgt image, 556 RoIs"},
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": "RoIs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "the reference's CUDA path cannot load on torch 2.x (torch.utils.ffi) and its CPU RoIAlign "
+                "backward / nms_cpu are wrong (SURVEY.md 8c), so the CPU arm is the oracle port of its kernels",
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="tlod", choices=["tlod", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cfg3", action="store_true", help="skip the cfg3-scale RoIAlign roofline section")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_tlod(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -50,6 +50,17 @@ const char* tlod_error_string(int code);
 /* Number of kernel launches enqueued by this library in this process (bench.py's `gpu_launches`). */
 unsigned long long tlod_launch_count(void);
 
+/* Optional per-kernel timing used by bench.py: while enabled, every kernel this
+ * library launches is bracketed by two CUDA events on its stream.
+ * tlod_profile_collect() waits for them (the one call here that synchronises the
+ * host) and returns the number of distinct kernel names; tlod_profile_get() reads
+ * entry `index`: name (static storage until the next reset), summed device time in
+ * milliseconds and number of launches. */
+void tlod_profile_enable(int on);
+void tlod_profile_reset(void);
+int tlod_profile_collect(void);
+int tlod_profile_get(int index, const char** name, double* total_ms, long long* launches);
+
 /* ------------------------------------------------------------------------ */
 /* RoIAlign                                                                   */
 /* replaces roi_align_forward_cuda / roi_align_backward_cuda                  */

@@ -1,0 +1,176 @@
+"""GPU parity: RoIAlign / RoIPool through the C ABI against the oracle.
+Tolerances are BASELINE.json's: forward 1e-5, atomics/scatter backward 1e-4 (relative to
+the largest reference magnitude); RoIPool values and argmax are exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+from oracle.synth import synth_rois
+from util import bits_equal, edge_rois, features, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+# (B, C, H, W, R, AH, AW, scale): plane-resident fast path (AW == 8), plane-resident
+# generic sampling (7x7, 3x5), and shapes that fall back to the generic kernels
+ALIGN_CASES = {
+    "cfg1_vgg_conv5": (1, 64, 37, 75, 128, 8, 8, 1 / 16),
+    "multi_image_res_conv4": (4, 32, 38, 75, 200, 8, 8, 1 / 16),
+    "raw_7x7": (2, 16, 20, 31, 64, 7, 7, 1 / 16),
+    "odd_grid_3x5": (2, 16, 13, 17, 40, 3, 5, 1 / 8),
+    "channels_not_x16": (2, 5, 20, 31, 64, 8, 8, 1 / 16),
+    "plane_too_big_for_smem": (1, 16, 150, 300, 24, 8, 8, 1 / 4),
+    "aligned_14x14": (1, 16, 38, 75, 32, 14, 14, 1 / 16),
+    "many_rois_one_image": (1, 16, 37, 75, 1300, 8, 8, 1 / 16),   # > one RoI-list refill
+    "aligned_16x8": (2, 32, 38, 75, 48, 16, 8, 1 / 16),           # tallest tile of the planes path
+    "full_planes_no_bands": (20, 256, 20, 31, 400, 8, 8, 1 / 16), # enough (image, slab) pairs for 1 band
+}
+
+
+def _case(tag):
+    B, C, H, W, R, AH, AW, scale = ALIGN_CASES[tag]
+    feat = features(B, C, H, W, 11)
+    rois = edge_rois(synth_rois(R, B, 12, im_h=int(H / scale), im_w=int(W / scale)), H, W, scale)
+    return feat, rois, AH, AW, scale
+
+
+@pytest.mark.parametrize("tag", list(ALIGN_CASES))
+def test_roi_align_forward(tag):
+    from tlod_b200 import functional as F
+    feat, rois, AH, AW, scale = _case(tag)
+    out = F.roi_align_forward(feat.to(DEV), rois.to(DEV), AH, AW, scale).cpu().numpy()
+    ref = orc.roi_align_forward(feat.numpy(), rois.numpy(), AH, AW, scale)
+    assert rel_err(out, ref) <= 1e-5
+    assert np.allclose(out, ref, rtol=1e-5, atol=1e-5)
+    # exactly-zero pattern (out-of-range samples) must match
+    assert np.array_equal(ref == 0, out == 0) or np.abs(out[ref == 0]).max() <= 1e-6
+
+
+@pytest.mark.parametrize("tag", list(ALIGN_CASES))
+def test_roi_align_backward(tag):
+    from tlod_b200 import functional as F
+    feat, rois, AH, AW, scale = _case(tag)
+    g = torch.Generator().manual_seed(5)
+    top = torch.randn(rois.size(0), feat.size(1), AH, AW, generator=g)
+    grad = F.roi_align_backward(top.to(DEV), rois.to(DEV), feat.shape, scale).cpu().numpy()
+    ref = orc.roi_align_backward(top.numpy(), rois.numpy(), feat.shape, scale, accumulate_double=True)
+    assert rel_err(grad, ref) <= 1e-4
+    ref32 = orc.roi_align_backward(top.numpy(), rois.numpy(), feat.shape, scale, accumulate_double=False)
+    assert rel_err(grad, ref32) <= 1e-4
+
+
+def test_roi_align_invalid_batch_index_gives_zeros():
+    from tlod_b200 import functional as F
+    feat, rois, AH, AW, scale = _case("multi_image_res_conv4")
+    rois[7, 0] = 9.0
+    rois[8, 0] = -1.0
+    out = F.roi_align_forward(feat.to(DEV), rois.to(DEV), AH, AW, scale).cpu().numpy()
+    assert np.all(out[7] == 0) and np.all(out[8] == 0)
+    keep = [i for i in range(rois.size(0)) if i not in (7, 8)]
+    ref = orc.roi_align_forward(feat.numpy(), rois.numpy()[keep], AH, AW, scale)
+    assert rel_err(out[keep], ref) <= 1e-5
+
+
+def test_roi_align_unsorted_and_empty_images():
+    """RoIs in arbitrary image order, one image without any RoI."""
+    from tlod_b200 import functional as F
+    feat = features(5, 32, 37, 75, 3)
+    rois = synth_rois(300, 5, 4)
+    rois[rois[:, 0] == 2, 0] = 4.0  # image 2 gets nothing
+    out = F.roi_align_forward(feat.to(DEV), rois.to(DEV), 8, 8, 1 / 16).cpu().numpy()
+    ref = orc.roi_align_forward(feat.numpy(), rois.numpy(), 8, 8, 1 / 16)
+    assert rel_err(out, ref) <= 1e-5
+    top = torch.randn(300, 32, 8, 8, generator=torch.Generator().manual_seed(1))
+    grad = F.roi_align_backward(top.to(DEV), rois.to(DEV), feat.shape, 1 / 16).cpu().numpy()
+    refg = orc.roi_align_backward(top.numpy(), rois.numpy(), feat.shape, 1 / 16, accumulate_double=True)
+    assert rel_err(grad, refg) <= 1e-4
+    assert np.all(grad[2] == 0)
+
+
+def test_roi_align_modules_and_autograd():
+    """RoIAlignAvg / RoIAlignMax / ROIAlign alias through autograd (modules/roi_align.py:26-42)."""
+    from model.roi_align.modules.roi_align import RoIAlign, RoIAlignAvg, RoIAlignMax
+    from model.roi_layers import ROIAlign
+    feat, rois, _, _, scale = _case("cfg1_vgg_conv5")
+    ref8 = torch.from_numpy(orc.roi_align_forward(feat.numpy(), rois.numpy(), 8, 8, scale))
+    fd = feat.to(DEV).requires_grad_(True)
+    avg = RoIAlignAvg(7, 7, scale)(fd, rois.to(DEV))
+    assert avg.shape == (rois.size(0), feat.size(1), 7, 7)
+    assert rel_err(avg.detach().cpu().numpy(), torch.nn.functional.avg_pool2d(ref8, 2, 1).numpy()) <= 1e-5
+    mx = RoIAlignMax(7, 7, scale)(fd, rois.to(DEV))
+    assert rel_err(mx.detach().cpu().numpy(), torch.nn.functional.max_pool2d(ref8, 2, 1).numpy()) <= 1e-5
+    raw = RoIAlign(8, 8, scale)(fd, rois.to(DEV))
+    assert rel_err(raw.detach().cpu().numpy(), ref8.numpy()) <= 1e-5
+    alias = ROIAlign((7, 7), scale, 0)(fd, rois.to(DEV))
+    assert torch.equal(alias, avg)
+    top = torch.randn(avg.shape, generator=torch.Generator().manual_seed(2))
+    avg.backward(top.to(DEV))
+    # reference chain on CPU: avg_pool2d backward, then the oracle's RoIAlign backward
+    r8 = ref8.clone().requires_grad_(True)
+    torch.nn.functional.avg_pool2d(r8, 2, 1).backward(top)
+    refg = orc.roi_align_backward(r8.grad.numpy(), rois.numpy(), feat.shape, scale, accumulate_double=True)
+    assert rel_err(fd.grad.cpu().numpy(), refg) <= 1e-4
+
+
+POOL_CASES = {
+    "vgg_conv5_7x7": (2, 32, 37, 75, 96, 7, 7, 1 / 16),
+    "pa_atf_conv3_stride4": (1, 8, 150, 300, 20, 7, 7, 1 / 4),
+    "pa_atf_conv4_stride8": (1, 16, 75, 150, 20, 7, 7, 1 / 8),
+    "odd_3x5": (3, 5, 13, 17, 40, 3, 5, 1 / 8),
+}
+
+
+@pytest.mark.parametrize("tag", list(POOL_CASES))
+def test_roi_pool_forward_backward(tag):
+    from tlod_b200 import functional as F
+    B, C, H, W, R, PH, PW, scale = POOL_CASES[tag]
+    feat = features(B, C, H, W, 21)
+    rois = edge_rois(synth_rois(R, B, 22, im_h=int(H / scale), im_w=int(W / scale)), H, W, scale)
+    out, arg = F.roi_pool_forward(feat.to(DEV), rois.to(DEV), PH, PW, scale)
+    ref, ref_arg = orc.roi_pool_forward(feat.numpy(), rois.numpy(), PH, PW, scale)
+    assert bits_equal(out.cpu().numpy(), ref)
+    assert np.array_equal(arg.cpu().numpy(), ref_arg)
+    top = torch.randn(out.shape, generator=torch.Generator().manual_seed(23))
+    grad = F.roi_pool_backward(top.to(DEV), arg, rois.to(DEV), feat.shape, scale).cpu().numpy()
+    refg = orc.roi_pool_backward(top.numpy(), ref_arg, rois.numpy(), feat.shape, scale)
+    assert rel_err(grad, refg) <= 1e-4
+    assert np.array_equal(grad == 0, refg == 0) or np.abs(grad[refg == 0]).max() < 1e-5
+
+
+def test_roi_pool_module_autograd():
+    from model.roi_pooling.modules.roi_pool import _RoIPooling
+    B, C, H, W, R, PH, PW, scale = POOL_CASES["vgg_conv5_7x7"]
+    feat = features(B, C, H, W, 31)
+    rois = synth_rois(R, B, 32)
+    fd = feat.to(DEV).requires_grad_(True)
+    out = _RoIPooling(PH, PW, scale)(fd, rois.to(DEV))
+    out.sum().backward()
+    ref, ref_arg = orc.roi_pool_forward(feat.numpy(), rois.numpy(), PH, PW, scale)
+    refg = orc.roi_pool_backward(np.ones_like(ref), ref_arg, rois.numpy(), feat.shape, scale)
+    assert bits_equal(out.detach().cpu().numpy(), ref)
+    assert rel_err(fd.grad.cpu().numpy(), refg) <= 1e-4
+
+
+def test_full_size_adjointness_cfg3():
+    """BASELINE cfg3 (8x1024x38x75, 2048 RoIs): too big for the CPU oracle in seconds, so check
+    the size-independent property <fwd(x), g> == <x, bwd(g)> and partition of unity."""
+    from tlod_b200 import functional as F
+    torch.manual_seed(0)
+    B, C, H, W, R = 8, 1024, 38, 75, 2048
+    x = torch.relu(torch.randn(B, C, H, W, device=DEV))
+    rois = synth_rois(R, B, 41).to(DEV)
+    y = F.roi_align_forward(x, rois, 8, 8, 1 / 16)
+    g = torch.randn_like(y)
+    gx = F.roi_align_backward(g, rois, x.shape, 1 / 16)
+    lhs = (y.double() * g.double()).sum().item()
+    rhs = (x.double() * gx.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-6 * max(abs(lhs), abs(rhs), 1.0) + 1e-3
+    ones = F.roi_align_forward(torch.ones_like(x), rois, 8, 8, 1 / 16)
+    nz = ones != 0
+    assert (ones[nz] - 1).abs().max().item() <= 1e-5  # weights of every valid sample sum to 1
+    # spot-check 16 RoIs x 8 channels of the big problem against the oracle
+    idx = torch.arange(0, R, R // 16)[:16]
+    sub = rois[idx].cpu()
+    ref = orc.roi_align_forward(x[:, :8].cpu().numpy(), sub.numpy(), 8, 8, 1 / 16)
+    assert rel_err(y[idx][:, :8].cpu().numpy(), ref) <= 1e-5

@@ -254,9 +254,11 @@ extern "C" int tlod_bbox_overlaps_batch(const float* anchors, int anchors_batche
   if ((long long)n * k == 0) return TLOD_OK;
   const long long per = (long long)n * k;
   dim3 grid((unsigned)((per + 255) / 256), batch);
-  overlaps_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(anchors, anchors_batched, anchor_stride,
-                                                          anchor_offset, gt, gt_stride, overlaps, n, k);
-  count_launch();
+  {
+    LaunchScope scope("overlaps_kernel", (cudaStream_t)stream);
+    overlaps_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(anchors, anchors_batched, anchor_stride,
+                                                            anchor_offset, gt, gt_stride, overlaps, n, k);
+  }
   return last_launch_status();
 }
 
@@ -266,8 +268,10 @@ extern "C" int tlod_bbox_transform_batch(const float* ex_rois, int ex_batched, c
   if (batch <= 0 || n < 0 || batch > 65535) return TLOD_ERR_BAD_SHAPE;
   if (n == 0) return TLOD_OK;
   dim3 grid((n + 255) / 256, batch);
-  transform_batch_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ex_rois, ex_batched, gt_rois, targets, n);
-  count_launch();
+  {
+    LaunchScope scope("transform_batch_kernel", (cudaStream_t)stream);
+    transform_batch_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ex_rois, ex_batched, gt_rois, targets, n);
+  }
   return last_launch_status();
 }
 
@@ -278,8 +282,10 @@ extern "C" int tlod_bbox_transform_inv_clip(const float* boxes, int boxes_batche
   if (batch <= 0 || n < 0 || batch > 65535) return TLOD_ERR_BAD_SHAPE;
   if (n == 0) return TLOD_OK;
   dim3 grid((n + 255) / 256, batch);
-  transform_inv_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(boxes, boxes_batched, deltas, im_info, out, n);
-  count_launch();
+  {
+    LaunchScope scope("transform_inv_kernel", (cudaStream_t)stream);
+    transform_inv_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(boxes, boxes_batched, deltas, im_info, out, n);
+  }
   return last_launch_status();
 }
 
@@ -290,8 +296,10 @@ extern "C" int tlod_clip_boxes(float* boxes, const float* im_info, int batch, in
   const long long per = (long long)n * 4 * k;
   if (per == 0) return TLOD_OK;
   dim3 grid((unsigned)((per + 255) / 256), batch);
-  clip_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(boxes, im_info, per);
-  count_launch();
+  {
+    LaunchScope scope("clip_kernel", (cudaStream_t)stream);
+    clip_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(boxes, im_info, per);
+  }
   return last_launch_status();
 }
 
@@ -315,14 +323,18 @@ extern "C" int tlod_anchor_labels(const float* anchors, const float* gt, int gt_
   cudaError_t e = cudaMemsetAsync(gtmax, 0x80, (size_t)batch * k * sizeof(int), st);
   if (e != cudaSuccess) return (int)e;
   dim3 grid((n + 255) / 256, batch);
-  gt_max_kernel<<<grid, 256, 0, st>>>(anchors, gt, gt_stride, gtmax, n, k);
-  count_launch();
+  {
+    LaunchScope scope("gt_max_kernel", st);
+    gt_max_kernel<<<grid, 256, 0, st>>>(anchors, gt, gt_stride, gtmax, n, k);
+  }
   int rc = last_launch_status();
   if (rc) return rc;
-  anchor_labels_kernel<<<grid, 256, 0, st>>>(anchors, gt, gt_stride, gtmax, labels, argmax,
-                                             max_overlaps, n, k, negative_overlap, positive_overlap,
-                                             clobber_positives);
-  count_launch();
+  {
+    LaunchScope scope("anchor_labels_kernel", st);
+    anchor_labels_kernel<<<grid, 256, 0, st>>>(anchors, gt, gt_stride, gtmax, labels, argmax,
+                                               max_overlaps, n, k, negative_overlap, positive_overlap,
+                                               clobber_positives);
+  }
   return last_launch_status();
 }
 
@@ -342,10 +354,12 @@ extern "C" int tlod_anchor_targets_finalize(const float* labels, const int* argm
     return TLOD_ERR_BAD_SHAPE;
   const int total = num_anchors * height * width;
   dim3 grid((total + 255) / 256, batch);
-  anchor_finalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-      labels, argmax, anchors, gt, gt_stride, inv_index, labels_out, targets_out, inside_w_out,
-      outside_w_out, n, k, num_anchors, height, width, inside_weight, positive_weight,
-      negative_weight);
-  count_launch();
+  {
+    LaunchScope scope("anchor_finalize_kernel", (cudaStream_t)stream);
+    anchor_finalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        labels, argmax, anchors, gt, gt_stride, inv_index, labels_out, targets_out, inside_w_out,
+        outside_w_out, n, k, num_anchors, height, width, inside_weight, positive_weight,
+        negative_weight);
+  }
   return last_launch_status();
 }

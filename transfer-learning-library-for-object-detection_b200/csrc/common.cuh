@@ -22,6 +22,25 @@ const DeviceInfo& device_info();
 
 inline int last_launch_status() { return (int)cudaGetLastError(); }
 
+// Optional per-kernel timing (tlod_profile_*): when enabled, every launch is bracketed by
+// two CUDA events on its own stream; bench.py reads the accumulated durations.
+extern int g_profile_on;
+void profile_begin(const char* name, cudaStream_t st, void** token);
+void profile_end(void* token, cudaStream_t st);
+
+// RAII around one kernel launch: counts it and, if profiling is on, times it.
+struct LaunchScope {
+  cudaStream_t st;
+  void* token;
+  LaunchScope(const char* name, cudaStream_t s) : st(s), token(nullptr) {
+    count_launch();
+    if (g_profile_on) profile_begin(name, st, &token);
+  }
+  ~LaunchScope() {
+    if (token) profile_end(token, st);
+  }
+};
+
 constexpr int kWarp = 32;
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }

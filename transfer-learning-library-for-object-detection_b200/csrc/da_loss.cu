@@ -129,8 +129,10 @@ extern "C" int tlod_grl_backward(const float* grad, float* out, float alpha, lon
   if (n < 0) return TLOD_ERR_BAD_SHAPE;
   if (n == 0) return TLOD_OK;
   const long long threads = (n + 3) / 4;
-  grl_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(grad, out, -alpha, n);
-  count_launch();
+  {
+    LaunchScope scope("grl_kernel", (cudaStream_t)stream);
+    grl_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(grad, out, -alpha, n);
+  }
   return last_launch_status();
 }
 
@@ -140,9 +142,11 @@ extern "C" int tlod_grl_backward_weighted(const float* grad, const float* row_we
   if (rows < 0 || cols < 0) return TLOD_ERR_BAD_SHAPE;
   const long long n = (long long)rows * cols;
   if (n == 0) return TLOD_OK;
-  grl_weighted_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      grad, row_weight, out, -alpha, rows, cols);
-  count_launch();
+  {
+    LaunchScope scope("grl_weighted_kernel", (cudaStream_t)stream);
+    grl_weighted_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        grad, row_weight, out, -alpha, rows, cols);
+  }
   return last_launch_status();
 }
 
@@ -157,9 +161,11 @@ extern "C" int tlod_da_loss_forward(const float* img_score, const float* ins_pro
   if (!losses_out || (batch > 0 && !img_score) || (num_ins > 0 && !ins_prob)) return TLOD_ERR_NULL_POINTER;
   if (batch < 0 || height < 0 || width < 0 || num_ins < 0 || (domain_label != 0 && domain_label != 1))
     return TLOD_ERR_BAD_SHAPE;
-  da_loss_fwd_kernel<<<1, DA_THREADS, 0, (cudaStream_t)stream>>>(
-      img_score, ins_prob, ins_label, domain_label, losses_out, batch, height * width, num_ins);
-  count_launch();
+  {
+    LaunchScope scope("da_loss_fwd_kernel", (cudaStream_t)stream);
+    da_loss_fwd_kernel<<<1, DA_THREADS, 0, (cudaStream_t)stream>>>(
+        img_score, ins_prob, ins_label, domain_label, losses_out, batch, height * width, num_ins);
+  }
   return last_launch_status();
 }
 
@@ -177,9 +183,11 @@ extern "C" int tlod_da_loss_backward(const float* img_score, const float* ins_pr
   const long long cells = (long long)batch * height * width;
   const long long n = cells > num_ins ? cells : num_ins;
   if (n == 0) return TLOD_OK;
-  da_loss_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      img_score, ins_prob, ins_label, domain_label, losses_out, upstream, w_img, w_ins, w_cst,
-      grad_img_score, grad_ins_prob, batch, height * width, num_ins);
-  count_launch();
+  {
+    LaunchScope scope("da_loss_bwd_kernel", (cudaStream_t)stream);
+    da_loss_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        img_score, ins_prob, ins_label, domain_label, losses_out, upstream, w_img, w_ins, w_cst,
+        grad_img_score, grad_ins_prob, batch, height * width, num_ins);
+  }
   return last_launch_status();
 }

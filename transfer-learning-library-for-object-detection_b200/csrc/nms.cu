@@ -112,9 +112,41 @@ __device__ __forceinline__ unsigned long long warp_or_u64(unsigned long long v) 
   return ((unsigned long long)hi << 32) | lo;
 }
 
+// OR of mask[(row0 + b) * ncb + j] over the set bits b of `bits`, at most 8 loads at a time
+// in flight (the loads are independent; a plain loop would serialise on L2 latency).
+__device__ __forceinline__ unsigned long long or_rows(const unsigned long long* __restrict__ m,
+                                                      int ncb, int row0, int j,
+                                                      unsigned long long bits) {
+  unsigned long long acc = 0ULL;
+  while (bits) {
+    unsigned long long v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      v[u] = 0ULL;
+      if (bits) {
+        const int b = __ffsll((long long)bits) - 1;
+        bits &= bits - 1ULL;
+        v[u] = m[(size_t)(row0 + b) * ncb + j];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc |= v[u];
+  }
+  return acc;
+}
+
 // keep_out[img * keep_stride + r] = r-th kept index (ascending), num_out[img] = count
 // (<= max_keep).  If rois_out != NULL also writes the reference's padded
 // (post, 5) block for the image: column 0 = image index, rows [0, count) = boxes.
+//
+// Chunk c = boxes [64c, 64c+64).  Warp 0 resolves the chunks in order; the suppression
+// word of chunk c is
+//     remv[c]                      rows of survivors of chunks <= c-3   (other warps, below)
+//   | OR survivors(c-1) of mask[row][c]   "s1", prefetched by warp 0 before it knew the survivors
+//   | OR survivors(c-2) of mask[row][c]   "s2", likewise
+// so the only serial work per chunk is the in-register resolve of the 64x64 diagonal block.
+// The other 7 warps fold the rows of chunk c's survivors into remv[j >= c+3]; their loads are
+// issued in iteration c and consumed in iteration c+1, two barriers before warp 0 needs them.
 __global__ void __launch_bounds__(SCAN_THREADS)
     nms_scan_kernel(const unsigned long long* __restrict__ mask, int n, int max_keep,
                     int* __restrict__ keep_out, int keep_stride, int* __restrict__ num_out,
@@ -123,6 +155,7 @@ __global__ void __launch_bounds__(SCAN_THREADS)
   extern __shared__ unsigned long long remv[];  // ncb words
   __shared__ unsigned long long kept_sh[2];
   __shared__ int done_sh[2];
+  constexpr int HELPERS = SCAN_THREADS - 32;
   const int img = blockIdx.x;
   const int ncb = (n + 63) >> 6;
   const unsigned long long* m = mask + (size_t)img * n * ncb;
@@ -131,31 +164,43 @@ __global__ void __launch_bounds__(SCAN_THREADS)
   for (int j = tid; j < ncb; j += SCAN_THREADS) remv[j] = 0ULL;
   __syncthreads();
 
-  int nkeep = 0;  // tracked by warp 0
-  // diagonal words of chunk c (d0: row 64c+lane, d1: row 64c+32+lane) and
-  // super-diagonal words of chunk c-1 at word c (s0, s1), prefetched one chunk ahead
-  unsigned long long d0 = 0, d1 = 0, s0 = 0, s1 = 0;
+  // ---- warp 0 state ----
+  int nkeep = 0;
+  unsigned long long d0 = 0, d1 = 0;      // diagonal words of the current chunk (rows lane, lane+32)
+  unsigned long long s1a = 0, s1b = 0;    // rows of chunk c-1 at word c
+  unsigned long long s2a = 0, s2b = 0;    // rows of chunk c-2 at word c
+  unsigned long long kept1 = 0ULL, kept2 = 0ULL;  // survivors of chunks c-1, c-2
   if (wid == 0 && ncb > 0) {
     if (lane < n) d0 = m[(size_t)lane * ncb];
     if (lane + 32 < n) d1 = m[(size_t)(lane + 32) * ncb];
   }
-  unsigned long long kept_prev = 0ULL;
+  // ---- helper state: word owned this round and its loads in flight ----
+  int pend_j = -1;
+  unsigned long long pend[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) pend[u] = 0ULL;
 
   for (int c = 0; c < ncb; ++c) {
     if (wid == 0) {
-      // prefetch for chunk c+1 before the latency-bound resolve
-      unsigned long long nd0 = 0, nd1 = 0, ns0 = 0, ns1 = 0;
-      if (c + 1 < ncb) {
-        const int r0 = 64 * (c + 1) + lane, r1 = r0 + 32;
-        if (r0 < n) nd0 = m[(size_t)r0 * ncb + c + 1];
-        if (r1 < n) nd1 = m[(size_t)r1 * ncb + c + 1];
-        ns0 = m[(size_t)(64 * c + lane) * ncb + c + 1];  // rows of chunk c are < n here
-        if (64 * c + 32 + lane < n) ns1 = m[(size_t)(64 * c + 32 + lane) * ncb + c + 1];
+      // prefetch everything chunk c+1 will need that does not depend on decisions
+      unsigned long long nd0 = 0, nd1 = 0, n1a = 0, n1b = 0, n2a = 0, n2b = 0;
+      if (c + 1 < ncb) {  // then chunks <= c are full: all their rows exist
+        const int w1 = c + 1;
+        const int r0 = 64 * w1 + lane, r1 = r0 + 32;
+        if (r0 < n) nd0 = m[(size_t)r0 * ncb + w1];
+        if (r1 < n) nd1 = m[(size_t)r1 * ncb + w1];
+        n1a = m[(size_t)(64 * c + lane) * ncb + w1];
+        n1b = m[(size_t)(64 * c + 32 + lane) * ncb + w1];
+        if (c >= 1) {
+          n2a = m[(size_t)(64 * (c - 1) + lane) * ncb + w1];
+          n2b = m[(size_t)(64 * (c - 1) + 32 + lane) * ncb + w1];
+        }
       }
-      // suppression of chunk c by the survivors of chunk c-1 (speculative words)
       unsigned long long urgent = 0ULL;
-      if ((kept_prev >> lane) & 1ULL) urgent |= s0;
-      if ((kept_prev >> (lane + 32)) & 1ULL) urgent |= s1;
+      if ((kept1 >> lane) & 1ULL) urgent |= s1a;
+      if ((kept1 >> (lane + 32)) & 1ULL) urgent |= s1b;
+      if ((kept2 >> lane) & 1ULL) urgent |= s2a;
+      if ((kept2 >> (lane + 32)) & 1ULL) urgent |= s2b;
       urgent = warp_or_u64(urgent);
       const unsigned long long cur = remv[c] | urgent;
       const int rows = min(64, n - 64 * c);
@@ -170,42 +215,55 @@ __global__ void __launch_bounds__(SCAN_THREADS)
         alive &= ~(1ULL << b);
       }
       // emit indices (ascending) up to max_keep
-      {
-        const int bit0 = lane, bit1 = lane + 32;
-        if ((kept >> bit0) & 1ULL) {
-          const int r = nkeep + __popcll(kept & ((1ULL << bit0) - 1ULL));
-          if (r < max_keep) keep[r] = 64 * c + bit0;
-        }
-        if ((kept >> bit1) & 1ULL) {
-          const int r = nkeep + __popcll(kept & ((1ULL << bit1) - 1ULL));
-          if (r < max_keep) keep[r] = 64 * c + bit1;
-        }
+      if ((kept >> lane) & 1ULL) {
+        const int r = nkeep + __popcll(kept & ((1ULL << lane) - 1ULL));
+        if (r < max_keep) keep[r] = 64 * c + lane;
+      }
+      if ((kept >> (lane + 32)) & 1ULL) {
+        const int r = nkeep + __popcll(kept & ((1ULL << (lane + 32)) - 1ULL));
+        if (r < max_keep) keep[r] = 64 * c + lane + 32;
       }
       nkeep += __popcll(kept);
       if (lane == 0) {
         kept_sh[c & 1] = kept;
         done_sh[c & 1] = (nkeep >= max_keep) ? 1 : 0;
       }
-      kept_prev = kept;
-      d0 = nd0; d1 = nd1; s0 = ns0; s1 = ns1;
+      kept2 = kept1;
+      kept1 = kept;
+      d0 = nd0; d1 = nd1;
+      s1a = n1a; s1b = n1b; s2a = n2a; s2b = n2b;
     }
     __syncthreads();
     if (done_sh[c & 1]) break;
     if (wid != 0) {
-      // OR the rows of this chunk's survivors into remv[j], j >= c + 2 (word c + 1 is
-      // covered by the speculative super-diagonal words above).  Thread-private words.
-      const unsigned long long kept = kept_sh[c & 1];
-      if (kept) {
-        for (int j = c + 2 + (tid - 32); j < ncb; j += SCAN_THREADS - 32) {
-          unsigned long long acc = 0ULL;
-          unsigned long long k = kept;
-          while (k) {
+      // consume the loads issued one iteration ago (rows of chunk c-1)
+      if (pend_j >= 0) {
+        unsigned long long acc = 0ULL;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc |= pend[u];
+        remv[pend_j] |= acc;
+        pend_j = -1;
+      }
+      // rows of chunk c's survivors -> words j >= c+3.  A word is always handled by the
+      // same thread (j mod HELPERS), so the read-modify-writes of remv never race.
+      unsigned long long k = kept_sh[c & 1];
+      const int t = tid - 32;
+      const int first = c + 3;
+      int j = first + ((t - first) % HELPERS + HELPERS) % HELPERS;
+      if (k && j < ncb) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          pend[u] = 0ULL;
+          if (k) {
             const int b = __ffsll((long long)k) - 1;
             k &= k - 1ULL;
-            acc |= m[(size_t)(64 * c + b) * ncb + j];
+            pend[u] = m[(size_t)(64 * c + b) * ncb + j];
           }
-          remv[j] |= acc;
         }
+        pend_j = j;
+        if (k) remv[j] |= or_rows(m, ncb, 64 * c, j, k);  // more than 8 survivors in the chunk
+        const unsigned long long all = kept_sh[c & 1];
+        for (j += HELPERS; j < ncb; j += HELPERS) remv[j] |= or_rows(m, ncb, 64 * c, j, all);
       }
     }
   }
@@ -421,16 +479,20 @@ static int launch_mask_scan(const float* boxes, int batch, int n, int stride, fl
   if (ncb > 65535 || batch > 65535) return TLOD_ERR_UNSUPPORTED;
   dim3 grid(ncb, ncb, batch);
   const bool filter = thresh >= 1e-6f && thresh <= 1e6f;
-  if (filter)
-    nms_mask_kernel<true><<<grid, 64, 0, st>>>(boxes, n, stride, thresh, mask);
-  else
-    nms_mask_kernel<false><<<grid, 64, 0, st>>>(boxes, n, stride, thresh, mask);
-  count_launch();
+  {
+    LaunchScope scope("nms_mask_kernel", st);
+    if (filter)
+      nms_mask_kernel<true><<<grid, 64, 0, st>>>(boxes, n, stride, thresh, mask);
+    else
+      nms_mask_kernel<false><<<grid, 64, 0, st>>>(boxes, n, stride, thresh, mask);
+  }
   int rc = last_launch_status();
   if (rc) return rc;
-  nms_scan_kernel<<<batch, SCAN_THREADS, (size_t)ncb * 8, st>>>(mask, n, max_keep, keep, keep_stride,
-                                                              num, boxes, stride, rois_out, post);
-  count_launch();
+  {
+    LaunchScope scope("nms_scan_kernel", st);
+    nms_scan_kernel<<<batch, SCAN_THREADS, (size_t)ncb * 8, st>>>(mask, n, max_keep, keep, keep_stride,
+                                                                num, boxes, stride, rois_out, post);
+  }
   return last_launch_status();
 }
 
@@ -524,10 +586,12 @@ extern "C" int tlod_proposals(const float* scores, const float* deltas, const fl
   cudaError_t e = cudaFuncSetAttribute(proposal_topk_decode_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  proposal_topk_decode_kernel<<<batch, TK_THREADS, smem, st>>>(
-      scores, deltas, im_info, anchors, num_anchors, height, width, feat_stride, n, n_pad,
-      (unsigned long long*)(base + w.sortbuf), boxes, order_out);
-  count_launch();
+  {
+    LaunchScope scope("proposal_topk_decode_kernel", st);
+    proposal_topk_decode_kernel<<<batch, TK_THREADS, smem, st>>>(
+        scores, deltas, im_info, anchors, num_anchors, height, width, feat_stride, n, n_pad,
+        (unsigned long long*)(base + w.sortbuf), boxes, order_out);
+  }
   int rc = last_launch_status();
   if (rc) return rc;
   return launch_mask_scan(boxes, batch, n, 4, nms_thresh, post_nms_topN, mask, keep, post_nms_topN,

@@ -340,6 +340,199 @@ __global__ void __launch_bounds__(PR_THREADS, 1)
 }
 
 // ===========================================================================
+// plane-resident backward (no atomics)
+// ===========================================================================
+// One CTA owns the gradient planes of (image, 16-channel slab, row band) exclusively: they
+// are accumulated in shared memory and written to HBM once with plain coalesced stores, so
+// bottom_grad needs neither a memset nor a single atomic (the reference issues
+// 4 * R * C * AH * AW global fp32 REDs, roi_align_kernel.cu:131-134).
+//
+// Inside the CTA the 16 warps never touch the same cell: warp w owns the plane rows
+// y == w (mod 16) of the band.  A RoI contributes 2*AH "row entries" (ph, dy) -> row
+// hs[ph] + dy; each entry is scattered by the one warp that owns that row, lane =
+// 2*channel + slot, slot = half of the 8 samples of the row.  As in the forward the plane
+// stride is 2 (mod 4) and the two slots update cells of opposite column parity, so every
+// read-modify-write instruction is bank-conflict free.  The order of additions into a cell
+// is fixed (RoI index, then ph, dy, pw), so the result is bitwise reproducible.
+//
+// The (16, AH, 8) gradient tiles of the next PB_NB RoIs are fetched with cp.async into a
+// second shared-memory stage while the current batch is scattered.
+constexpr int PB_NB = 4;      // RoIs per batch (stage)
+constexpr int PB_LIST = 512;  // RoI indices per refill
+
+struct PBShared {
+  int list[PB_LIST];
+  int warp_sums[PR_THREADS / 32];
+  AxisTab rows[2][PB_NB][PR_MAXA];  // off = first row index (not scaled) or -1
+  AxisTab cols[2][PB_NB][PR_MAXA];
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// RoIs of image `img` whose sampled rows can intersect [y_lo, y_hi), ranks [lo, hi) -> list
+__device__ inline int pb_build_list(PBShared& sh, const float* __restrict__ rois, int R, int img,
+                                    int AH, int H, float scale, int y_lo, int y_hi, int lo, int hi) {
+  int running = 0;
+  for (int base = 0; base < R; base += PR_THREADS) {
+    const int i = base + threadIdx.x;
+    bool m = false;
+    if (i < R) {
+      const float* r = rois + (size_t)i * 5;
+      if ((int)__ldg(r) == img) {
+        const AlignAxis a0 = align_axis(__ldg(r + 2), __ldg(r + 4), scale, AH, H, 0);
+        const AlignAxis a1 = align_axis(__ldg(r + 2), __ldg(r + 4), scale, AH, H, AH - 1);
+        m = (a0.start < y_hi) && (a1.start + 1 >= y_lo);
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, m);
+    if (lane_id() == 0) sh.warp_sums[warp_id()] = __popc(bal);
+    __syncthreads();
+    int before = running, total = 0;
+#pragma unroll
+    for (int w = 0; w < PR_THREADS / 32; ++w) {
+      const int v = sh.warp_sums[w];
+      if (w < warp_id()) before += v;
+      total += v;
+    }
+    if (m) {
+      const int rank = before + __popc(bal & ((1u << lane_id()) - 1u));
+      if (rank >= lo && rank < hi) sh.list[rank - lo] = i;
+    }
+    running += total;
+    __syncthreads();
+  }
+  return running;  // number of matching RoIs in the whole array
+}
+
+__global__ void __launch_bounds__(PR_THREADS, 1)
+    roi_align_bwd_planes_kernel(const float* __restrict__ top_grad, const float* __restrict__ rois,
+                                float* __restrict__ bottom_grad, int B, int C, int H, int W, int R,
+                                int AH, float scale, int nsplit, int band_rows, int Ppb, int TS) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* planes = reinterpret_cast<float*>(smem_raw);
+  float* tiles = planes + (size_t)PR_CH * Ppb;                       // [2][PB_NB][16 * TS]
+  PBShared& sh = *reinterpret_cast<PBShared*>(tiles + 2 * PB_NB * PR_CH * TS);
+  const int tid = threadIdx.x, lane = lane_id(), wid = warp_id();
+  const int nslabs = C / PR_CH;
+  const int band = blockIdx.x % nsplit;
+  const int pair = blockIdx.x / nsplit;
+  const int img = pair / nslabs, c0 = (pair % nslabs) * PR_CH;
+  const int y_lo = band * band_rows, y_hi = min(H, y_lo + band_rows);
+  const int S = AH * 8, S4 = S / 4;
+  const int tile_floats = PR_CH * TS;
+
+  for (int i = tid; i < PR_CH * Ppb; i += PR_THREADS) planes[i] = 0.f;
+
+  const int c = lane >> 1, slot = lane & 1;
+  int done = 0, total = 1;
+  while (done < total) {
+    total = pb_build_list(sh, rois, R, img, AH, H, scale, y_lo, y_hi, done, done + PB_LIST);
+    const int cnt = min(PB_LIST, total - done);  // list entries valid this round
+    const int nbatch = (cnt + PB_NB - 1) / PB_NB;
+
+    auto issue = [&](int k) {  // gradient tiles of batch k -> stage k & 1
+      const int nb = min(PB_NB, cnt - k * PB_NB);
+      float* stage = tiles + (size_t)(k & 1) * PB_NB * tile_floats;
+      for (int q = tid; q < nb * PR_CH * S4; q += PR_THREADS) {
+        const int j = q / (PR_CH * S4);
+        const int rem = q - j * (PR_CH * S4);
+        const int ch = rem / S4, f = rem - ch * S4;
+        const int n = sh.list[k * PB_NB + j];
+        cp_async16(stage + j * tile_floats + ch * TS + f * 4,
+                   top_grad + ((size_t)n * C + c0 + ch) * S + f * 4);
+      }
+      cp_async_commit();
+    };
+
+    if (nbatch > 0) issue(0);
+    for (int k = 0; k < nbatch; ++k) {
+      const int nb = min(PB_NB, cnt - k * PB_NB);
+      if (k + 1 < nbatch) issue(k + 1);
+      // sampling tables of batch k
+      if (tid < nb * 32) {
+        const int j = tid >> 5, e = tid & 31;
+        const float* r = rois + (size_t)sh.list[k * PB_NB + j] * 5;
+        if (e < AH) {
+          const AlignAxis a = align_axis(__ldg(r + 2), __ldg(r + 4), scale, AH, H, e);
+          AxisTab t = make_tab(a, 1);
+          sh.rows[k & 1][j][e] = t;
+        } else if (e >= 16 && e < 24) {
+          sh.cols[k & 1][j][e - 16] = make_tab(align_axis(__ldg(r + 1), __ldg(r + 3), scale, 8, W, e - 16), 1);
+        }
+      }
+      if (k + 1 < nbatch) cp_async_wait<1>(); else cp_async_wait<0>();
+      __syncthreads();
+
+      const float* stage = tiles + (size_t)(k & 1) * PB_NB * tile_floats;
+      for (int j = 0; j < nb; ++j) {
+        const AxisTab* rows = sh.rows[k & 1][j];
+        const AxisTab* cols = sh.cols[k & 1][j];
+        // which of the 2*AH row entries (ph = lane >> 1, dy = lane & 1) does this warp own?
+        bool own = false;
+        if ((lane >> 1) < AH) {
+          const int r0 = rows[lane >> 1].off;
+          const int y = r0 + (lane & 1);
+          own = r0 >= 0 && y >= y_lo && y < y_hi && ((y - y_lo) & 15) == wid;
+        }
+        unsigned mine = __ballot_sync(0xffffffffu, own);
+        if (!mine) continue;
+        int cx[4], flip[4];
+        float cw0[4], cw1[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const AxisTab t = cols[4 * slot + q];
+          const int xp = cols[4 * (slot ^ 1) + q].off;
+          cx[q] = t.off;
+          cw0[q] = t.w0;
+          cw1[q] = t.w1;
+          // slot 1 swaps its (x, x+1) order when both slots start on the same parity
+          flip[q] = slot & (((t.off ^ xp) & 1) ^ 1);
+        }
+        const float* g_roi = stage + j * tile_floats + c * TS + 4 * slot;
+        while (mine) {
+          const int e = __ffs(mine) - 1;
+          mine &= mine - 1u;
+          const int ph = e >> 1, dy = e & 1;
+          const AxisTab rt = rows[ph];
+          const float rw = dy ? rt.w1 : rt.w0;
+          float* prow = planes + c * Ppb + (rt.off + dy - y_lo) * W;
+          const float4 g = *reinterpret_cast<const float4*>(g_roi + ph * 8);
+          const float gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float mv = rw * gv[q];
+            const int x = cx[q], f = flip[q];
+            if (x >= 0) prow[x + f] += mv * (f ? cw1[q] : cw0[q]);
+            __syncwarp();
+            if (x >= 0) prow[x + (f ^ 1)] += mv * (f ? cw0[q] : cw1[q]);
+            __syncwarp();
+          }
+        }
+      }
+      __syncthreads();  // stage k & 1 and tables k & 1 are free again
+    }
+    done += cnt;
+    if (cnt == 0) break;
+  }
+  __syncthreads();
+  // ---- write the band of the 16 planes: warp w stores channel w ----
+  {
+    const int n_cells = (y_hi - y_lo) * W;
+    float* g = bottom_grad + ((size_t)img * C + c0 + wid) * H * W + (size_t)y_lo * W;
+    const float* sp = planes + wid * Ppb;
+    for (int i = lane; i < n_cells; i += 32) g[i] = sp[i];
+  }
+}
+
+// ===========================================================================
 // host side
 // ===========================================================================
 static int check_common(const void* a, const void* b, const void* c, int batch, int channels,
@@ -370,13 +563,15 @@ static int generic_launch(bool backward, const float* src, const float* rois, fl
   while ((channels + cpb - 1) / cpb > 65535) ++cpb;
   dim3 grid(num_rois, (channels + cpb - 1) / cpb);
   size_t smem = sizeof(AxisTab) * (size_t)(ah + aw);
-  if (backward)
-    roi_align_generic_kernel<true><<<grid, 256, smem, st>>>(src, rois, dst, batch, channels, height,
-                                                            width, ah, aw, scale, cpb);
-  else
-    roi_align_generic_kernel<false><<<grid, 256, smem, st>>>(src, rois, dst, batch, channels,
-                                                             height, width, ah, aw, scale, cpb);
-  count_launch();
+  {
+    LaunchScope scope(backward ? "roi_align_bwd_generic_kernel" : "roi_align_fwd_generic_kernel", st);
+    if (backward)
+      roi_align_generic_kernel<true><<<grid, 256, smem, st>>>(src, rois, dst, batch, channels, height,
+                                                              width, ah, aw, scale, cpb);
+    else
+      roi_align_generic_kernel<false><<<grid, 256, smem, st>>>(src, rois, dst, batch, channels,
+                                                               height, width, ah, aw, scale, cpb);
+  }
   return last_launch_status();
 }
 
@@ -404,9 +599,11 @@ extern "C" int tlod_roi_align_forward(const float* features, const float* rois, 
     auto kern = fast8 ? roi_align_fwd_planes_kernel<true> : roi_align_fwd_planes_kernel<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    kern<<<grid, PR_THREADS, smem, st>>>(features, rois, output, batch, channels, height, width,
-                                         num_rois, aligned_h, aligned_w, spatial_scale, Pp);
-    count_launch();
+    {
+      LaunchScope scope("roi_align_fwd_planes_kernel", st);
+      kern<<<grid, PR_THREADS, smem, st>>>(features, rois, output, batch, channels, height, width,
+                                           num_rois, aligned_h, aligned_w, spatial_scale, Pp);
+    }
     return last_launch_status();
   }
   return generic_launch(false, features, rois, output, batch, channels, height, width, num_rois,
@@ -421,8 +618,43 @@ extern "C" int tlod_roi_align_backward(const float* top_grad, const float* rois,
                         aligned_h, aligned_w);
   if (rc != TLOD_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = cudaMemsetAsync(bottom_grad, 0,
-                                  (size_t)batch * channels * height * width * sizeof(float), st);
+  const size_t grad_bytes = (size_t)batch * channels * height * width * sizeof(float);
+  if (num_rois == 0) return (int)cudaMemsetAsync(bottom_grad, 0, grad_bytes, st);
+
+  // plane-resident path: AW == 8 (one float4 per slot), tiles fetched in 16-byte pieces
+  if (channels % PR_CH == 0 && aligned_w == 8 && aligned_h <= PR_MAXA &&
+      ((uintptr_t)top_grad & 15) == 0) {
+    const int pairs = batch * (channels / PR_CH);
+    const int sms = device_info().sm_count;
+    int nsplit = (2 * sms + pairs - 1) / pairs;  // row bands per plane: fill the machine twice over
+    if (nsplit > 4) nsplit = 4;
+    if (nsplit > height / 8) nsplit = height / 8 > 0 ? height / 8 : 1;
+    if (nsplit < 1) nsplit = 1;
+    const int S = aligned_h * 8;
+    const int TS = (S + 31) / 32 * 32 + 8;  // channel stride of a tile: 8 (mod 32) floats
+    for (; nsplit <= 64; ++nsplit) {  // more bands if the planes do not fit shared memory
+      const int band_rows = (height + nsplit - 1) / nsplit;
+      const int Ppb = pr_plane_stride(band_rows * width);
+      const size_t smem = ((size_t)PR_CH * Ppb + (size_t)2 * PB_NB * PR_CH * TS) * sizeof(float) +
+                          sizeof(PBShared);
+      if (smem > (size_t)device_info().max_smem_optin) {
+        if (band_rows <= 1) break;
+        continue;
+      }
+      if ((long long)pairs * nsplit > 2147483647LL) break;
+      cudaError_t e = cudaFuncSetAttribute(roi_align_bwd_planes_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      {
+        LaunchScope scope("roi_align_bwd_planes_kernel", st);
+        roi_align_bwd_planes_kernel<<<pairs * nsplit, PR_THREADS, smem, st>>>(
+            top_grad, rois, bottom_grad, batch, channels, height, width, num_rois, aligned_h,
+            spatial_scale, nsplit, band_rows, Ppb, TS);
+      }
+      return last_launch_status();
+    }
+  }
+  cudaError_t e = cudaMemsetAsync(bottom_grad, 0, grad_bytes, st);
   if (e != cudaSuccess) return (int)e;
   return generic_launch(true, top_grad, rois, bottom_grad, batch, channels, height, width, num_rois,
                         aligned_h, aligned_w, spatial_scale, st);

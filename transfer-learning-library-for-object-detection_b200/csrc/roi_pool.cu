@@ -149,10 +149,12 @@ extern "C" int tlod_roi_pool_forward(const float* features, const float* rois, f
   if (num_rois == 0) return TLOD_OK;
   int cpb;
   dim3 grid = pool_grid(num_rois, channels, pooled_h * pooled_w, &cpb);
-  roi_pool_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(features, rois, output, argmax, batch,
-                                                              channels, height, width, pooled_h,
-                                                              pooled_w, spatial_scale, cpb);
-  count_launch();
+  {
+    LaunchScope scope("roi_pool_fwd_kernel", (cudaStream_t)stream);
+    roi_pool_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(features, rois, output, argmax, batch,
+                                                                channels, height, width, pooled_h,
+                                                                pooled_w, spatial_scale, cpb);
+  }
   return last_launch_status();
 }
 
@@ -171,8 +173,10 @@ extern "C" int tlod_roi_pool_backward(const float* top_grad, const int* argmax, 
   if (num_rois == 0) return TLOD_OK;
   int cpb;
   dim3 grid = pool_grid(num_rois, channels, pooled_h * pooled_w, &cpb);
-  roi_pool_bwd_kernel<<<grid, 256, 0, st>>>(top_grad, argmax, rois, bottom_grad, batch, channels,
-                                            height, width, pooled_h, pooled_w, spatial_scale, cpb);
-  count_launch();
+  {
+    LaunchScope scope("roi_pool_bwd_kernel", st);
+    roi_pool_bwd_kernel<<<grid, 256, 0, st>>>(top_grad, argmax, rois, bottom_grad, batch, channels,
+                                              height, width, pooled_h, pooled_w, spatial_scale, cpb);
+  }
   return last_launch_status();
 }

@@ -19,6 +19,11 @@ SIGNATURES = {
     "tlod_version": (c_int, []),
     "tlod_error_string": (ctypes.c_char_p, [c_int]),
     "tlod_launch_count": (ctypes.c_ulonglong, []),
+    "tlod_profile_enable": (None, [c_int]),
+    "tlod_profile_reset": (None, []),
+    "tlod_profile_collect": (c_int, []),
+    "tlod_profile_get": (c_int, [c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_double),
+                                 ctypes.POINTER(c_longlong)]),
     "tlod_roi_align_forward": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P]),
     "tlod_roi_align_backward": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P]),
     "tlod_roi_pool_forward": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P]),
@@ -76,3 +81,25 @@ def check(rc: int, what: str) -> None:
 
 def launch_count() -> int:
     return int(lib.tlod_launch_count())
+
+
+def profile(enable: bool) -> None:
+    """Turn per-kernel event timing on/off (bench.py)."""
+    lib.tlod_profile_enable(1 if enable else 0)
+
+
+def profile_reset() -> None:
+    lib.tlod_profile_reset()
+
+
+def profile_read() -> dict:
+    """{kernel name: (total_ms, launches)}; synchronises the recorded events."""
+    n = lib.tlod_profile_collect()
+    out = {}
+    for i in range(n):
+        name = ctypes.c_char_p()
+        ms = ctypes.c_double()
+        cnt = c_longlong()
+        check(lib.tlod_profile_get(i, ctypes.byref(name), ctypes.byref(ms), ctypes.byref(cnt)), "tlod_profile_get")
+        out[name.value.decode()] = (ms.value, cnt.value)
+    return out
