@@ -67,6 +67,20 @@ int tlod_profile_get(int index, const char** name, double* total_ms, long long* 
 /*   lib/model/roi_align/src/roi_align_cuda.c:7-40, :42-76                    */
 /*   (kernels lib/model/roi_align/src/roi_align_kernel.cu:15-70, :94-143)     */
 /* ------------------------------------------------------------------------ */
+/* RoIAlign plan: everything that depends only on (rois, map geometry, aligned size):
+ * per-RoI sampling tables, the RoI indices stably sorted by image, per-image offsets and
+ * the backward column chains.  Build it once per `rois` tensor with tlod_roi_align_plan
+ * and pass it to the forward and the backward call (same batch, height, width, num_rois,
+ * aligned_h, aligned_w, spatial_scale).  `plan` must be 256-byte aligned and at least
+ * tlod_roi_align_plan_bytes(batch, num_rois) bytes.  Limits of the planned (shared-memory
+ * resident, atomic-free) kernels: batch <= 1024, aligned_h/w <= 16; outside them, or with
+ * plan == NULL, the forward/backward entry points use the generic kernels (one CTA per
+ * RoI and channel block; fp32 atomics in the backward). */
+size_t tlod_roi_align_plan_bytes(int batch, int num_rois);
+int tlod_roi_align_plan(const float* rois, int batch, int height, int width, int num_rois,
+                        int aligned_h, int aligned_w, float spatial_scale, void* plan,
+                        size_t plan_bytes, void* stream);
+
 /* features (batch, channels, height, width); rois (num_rois, 5) =
  * [batch_idx, x1, y1, x2, y2] in image pixels; output (num_rois, channels,
  * aligned_h, aligned_w).  One bilinear sample per output cell at
@@ -76,7 +90,8 @@ int tlod_profile_get(int index, const char** name, double* total_ms, long long* 
  * Requires height >= 2, width >= 2, aligned_h >= 2, aligned_w >= 2. */
 int tlod_roi_align_forward(const float* features, const float* rois, float* output, int batch,
                            int channels, int height, int width, int num_rois, int aligned_h,
-                           int aligned_w, float spatial_scale, void* stream);
+                           int aligned_w, float spatial_scale, const void* plan, size_t plan_bytes,
+                           void* stream);
 
 /* top_grad (num_rois, channels, aligned_h, aligned_w) -> bottom_grad (batch,
  * channels, height, width).  bottom_grad is fully OVERWRITTEN with the gradient
@@ -84,7 +99,8 @@ int tlod_roi_align_forward(const float* features, const float* rois, float* outp
  * functions/roi_align.py:42, so the observable result is the same). */
 int tlod_roi_align_backward(const float* top_grad, const float* rois, float* bottom_grad,
                             int batch, int channels, int height, int width, int num_rois,
-                            int aligned_h, int aligned_w, float spatial_scale, void* stream);
+                            int aligned_h, int aligned_w, float spatial_scale, const void* plan,
+                            size_t plan_bytes, void* stream);
 
 /* ------------------------------------------------------------------------ */
 /* RoIPool                                                                    */

@@ -36,7 +36,9 @@ def test_no_torch_types_in_the_abi():
 
 def test_argument_errors_are_returned_not_fatal():
     from tlod_b200._lib import lib
-    assert lib.tlod_roi_align_forward(None, None, None, 1, 16, 8, 8, 4, 8, 8, 0.0625, None) == -1
+    assert lib.tlod_roi_align_forward(None, None, None, 1, 16, 8, 8, 4, 8, 8, 0.0625, None, 0, None) == -1
+    assert lib.tlod_roi_align_plan(None, 1, 8, 8, 4, 8, 8, 0.0625, None, 0, None) == -1
+    assert lib.tlod_roi_align_plan_bytes(8, 2048) >= 2048 * (512 + 176 + 32 + 4)
     assert lib.tlod_nms(None, 5, 3, 0.7, 0, None, None, None, 0, None) == -1
     assert b"null" in lib.tlod_error_string(-1)
     assert lib.tlod_nms_workspace_bytes(12000) >= 12000 * 188 * 8

@@ -12,8 +12,9 @@ from util import bits_equal, edge_rois, features, rel_err
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
-# (B, C, H, W, R, AH, AW, scale): plane-resident fast path (AW == 8), plane-resident
-# generic sampling (7x7, 3x5), and shapes that fall back to the generic kernels
+# (B, C, H, W, R, AH, AW, scale): plane-resident forward (AW == 8 fast path and general
+# sampling 7x7 / 3x5 / 14x14), band-resident backward (AW == 8, C % 32 == 0), and shapes that
+# fall back to the generic kernels (channels % 16, planes too big for shared memory)
 ALIGN_CASES = {
     "cfg1_vgg_conv5": (1, 64, 37, 75, 128, 8, 8, 1 / 16),
     "multi_image_res_conv4": (4, 32, 38, 75, 200, 8, 8, 1 / 16),
@@ -24,7 +25,10 @@ ALIGN_CASES = {
     "aligned_14x14": (1, 16, 38, 75, 32, 14, 14, 1 / 16),
     "many_rois_one_image": (1, 16, 37, 75, 1300, 8, 8, 1 / 16),   # > one RoI-list refill
     "aligned_16x8": (2, 32, 38, 75, 48, 16, 8, 1 / 16),           # tallest tile of the planes path
-    "full_planes_no_bands": (20, 256, 20, 31, 400, 8, 8, 1 / 16), # enough (image, slab) pairs for 1 band
+    "full_planes_no_bands": (20, 256, 20, 31, 400, 8, 8, 1 / 16), # many (image, slab) pairs
+    "bwd_partial_channel_group": (2, 160, 20, 31, 64, 8, 8, 1 / 16),  # 128 + 32 channels
+    "bwd_one_warp_group": (3, 32, 38, 75, 96, 8, 8, 1 / 16),
+    "tall_tile_6x8": (2, 64, 37, 75, 80, 6, 8, 1 / 16),
 }
 
 
@@ -58,6 +62,50 @@ def test_roi_align_backward(tag):
     assert rel_err(grad, ref) <= 1e-4
     ref32 = orc.roi_align_backward(top.numpy(), rois.numpy(), feat.shape, scale, accumulate_double=False)
     assert rel_err(grad, ref32) <= 1e-4
+
+
+@pytest.mark.parametrize("tag", ["cfg1_vgg_conv5", "odd_grid_3x5", "bwd_partial_channel_group"])
+def test_roi_align_generic_kernels_without_plan(tag):
+    """plan == NULL: the generic (per-RoI CTA, atomics in the backward) kernels."""
+    from tlod_b200 import functional as F
+    feat, rois, AH, AW, scale = _case(tag)
+    out = F.roi_align_forward(feat.to(DEV), rois.to(DEV), AH, AW, scale, use_plan=False).cpu().numpy()
+    ref = orc.roi_align_forward(feat.numpy(), rois.numpy(), AH, AW, scale)
+    assert rel_err(out, ref) <= 1e-5
+    g = torch.Generator().manual_seed(5)
+    top = torch.randn(rois.size(0), feat.size(1), AH, AW, generator=g)
+    grad = F.roi_align_backward(top.to(DEV), rois.to(DEV), feat.shape, scale, use_plan=False).cpu().numpy()
+    refg = orc.roi_align_backward(top.numpy(), rois.numpy(), feat.shape, scale, accumulate_double=True)
+    assert rel_err(grad, refg) <= 1e-4
+
+
+def test_roi_align_small_and_huge_rois_column_chain():
+    """RoIs from sub-cell to whole-map size: every code of the backward column chain (same cell,
+    shift by one, jump) and the all-jump fast path; one plan shared by forward and backward."""
+    from tlod_b200 import functional as F
+    B, C, H, W, scale = 2, 64, 37, 75, 1 / 16
+    g = torch.Generator().manual_seed(21)
+    R = 600
+    wpx = torch.cat([torch.rand(200, generator=g) * 40, torch.rand(200, generator=g) * 200,
+                     torch.rand(200, generator=g) * 1300])
+    hpx = torch.cat([torch.rand(200, generator=g) * 30, torch.rand(200, generator=g) * 150,
+                     torch.rand(200, generator=g) * 700])[torch.randperm(R, generator=g)]
+    x1 = torch.rand(R, generator=g) * 1250 - 40
+    y1 = torch.rand(R, generator=g) * 640 - 30
+    rois = torch.stack([torch.randint(0, B, (R,), generator=g).float(), x1, y1, x1 + wpx, y1 + hpx], 1)
+    feat = features(B, C, H, W, 22)
+    top = torch.randn(R, C, 8, 8, generator=g)
+    rd = rois.to(DEV)
+    plan = F.roi_align_plan(rd, feat.shape, 8, 8, scale)
+    out = F.roi_align_forward(feat.to(DEV), rd, 8, 8, scale, plan=plan).cpu().numpy()
+    ref = orc.roi_align_forward(feat.numpy(), rois.numpy(), 8, 8, scale)
+    assert rel_err(out, ref) <= 1e-5
+    grad = F.roi_align_backward(top.to(DEV), rd, feat.shape, scale, plan=plan).cpu().numpy()
+    refg = orc.roi_align_backward(top.numpy(), rois.numpy(), feat.shape, scale, accumulate_double=True)
+    assert rel_err(grad, refg) <= 1e-4
+    # bitwise reproducible: no atomics, fixed summation order
+    grad2 = F.roi_align_backward(top.to(DEV), rd, feat.shape, scale, plan=plan).cpu().numpy()
+    assert np.array_equal(grad, grad2)
 
 
 def test_roi_align_invalid_batch_index_gives_zeros():

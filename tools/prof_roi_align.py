@@ -21,11 +21,34 @@ if what == "roi":
     rois = synth_rois(R, B, 41)
     rois = rois[torch.argsort(rois[:, 0], stable=True)].contiguous().to(dev)
     top = torch.randn(R, C, 8, 8, device=dev)
-    for _ in range(iters):
-        y = F.roi_align_forward(x, rois, 8, 8, 1 / 16)
-        g = F.roi_align_backward(top, rois, x.shape, 1 / 16)
-    torch.cuda.synchronize()
-    print("ok", float(y.sum()), float(g.sum()))
+    plan = F.roi_align_plan(rois, x.shape, 8, 8, 1 / 16)
+    alg = B * C * H * W * 4 + R * 20 + R * C * 64 * 4
+
+    def timed(fn, n):
+        for _ in range(3):
+            r = fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            r = fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n, r
+    if iters <= 3:  # ncu mode: few launches
+        for _ in range(iters):
+            plan = F.roi_align_plan(rois, x.shape, 8, 8, 1 / 16)
+            y = F.roi_align_forward(x, rois, 8, 8, 1 / 16, plan=plan)
+            g = F.roi_align_backward(top, rois, x.shape, 1 / 16, plan=plan)
+        torch.cuda.synchronize()
+        print("ok", float(y.sum()), float(g.sum()))
+    else:
+        tp, _ = timed(lambda: F.roi_align_plan(rois, x.shape, 8, 8, 1 / 16), iters)
+        tf, y = timed(lambda: F.roi_align_forward(x, rois, 8, 8, 1 / 16, plan=plan), iters)
+        tb, g = timed(lambda: F.roi_align_backward(top, rois, x.shape, 1 / 16, plan=plan), iters)
+        print("ok", float(y.sum()), float(g.sum()))
+        print("cfg3 plan %.1f us  fwd %.1f us (%.0f GB/s, %.3f of 6546)  bwd %.1f us (%.0f GB/s, %.3f)" % (
+            tp * 1e3, tf * 1e3, alg / tf / 1e6, alg / tf / 1e6 / 6546.2, tb * 1e3, alg / tb / 1e6, alg / tb / 1e6 / 6546.2))
 else:
     B, A, H, W = 2, 12, 37, 75
     prob, deltas = synth_rpn(B, A, H, W, 3)

@@ -3,24 +3,35 @@
 // Reference semantics: lib/model/roi_align/src/roi_align_kernel.cu:15-70 (fwd),
 // :94-143 (bwd); glue lib/model/roi_align/src/roi_align_cuda.c.
 //
-// Two families of kernels:
+// Three pieces:
 //
-//  * "plane-resident" kernels (the product path for every BASELINE shape): a CTA
-//    keeps the 16 feature planes of one (image, 16-channel slab) in shared
-//    memory (16 x H*W fp32 = 178-182 KB for the 37x75 / 38x75 maps) and
-//    streams the image's RoIs through them.  HBM traffic is then the
-//    algorithmic minimum: each plane is read (fwd) or written (bwd) once, the
-//    (R, C, AH, AW) tensor is streamed once with full-sector accesses.
-//    Lane mapping: lane = 2*channel + slot.  The plane stride is padded to
-//    2 (mod 4) floats so that the 16 channels land on the 16 even (or odd)
-//    banks; the two slots of a channel always touch cells of opposite column
-//    parity, so every shared-memory access of the gather/scatter is
-//    bank-conflict free regardless of the RoI geometry.
+//  * the *plan* (tlod_roi_align_plan): everything that depends only on the RoIs and the
+//    map geometry, computed once per `rois` tensor and shared by the forward and the
+//    backward call: per RoI the sampling tables of its AH rows and AW columns (cell offset,
+//    the two bilinear weights), the RoI indices stably sorted by image, per-image offsets,
+//    and for the backward the column "merge chain" that turns the 16 (possibly
+//    coinciding) column cells of a sample row into at most 16 *distinct* cells.
 //
-//  * generic kernels for shapes the plane-resident layout cannot hold
-//    (channels % 16 != 0, planes too large for shared memory, aligned size
-//    > 16): one CTA per (RoI, channel block), geometry hoisted to shared
-//    memory, coalesced output, fp32 atomics in the backward.
+//  * plane-resident forward: a CTA keeps the 16 feature planes of one (image, 16-channel
+//    slab) in shared memory (16 x H*W fp32 = 178-182 KB for the 37x75 / 38x75 maps) and
+//    streams the image's RoIs through them.  HBM traffic is the algorithmic minimum: each
+//    plane is read once, the (R, C, AH, AW) tensor is written once with full 32-byte
+//    sectors.  Lane = 2*channel + slot; slot = half of an output row (4 samples).  The
+//    plane stride is 2 (mod 4) floats so the 16 channels land on 16 banks of one parity,
+//    and the two slots always read cells of opposite column parity, so every shared-memory
+//    gather is bank-conflict free for any RoI geometry.
+//
+//  * band-resident backward (no global atomics, no memset): a CTA owns the gradient planes
+//    of (image, 128-channel group, row band) in shared memory.  Lane = channel: a plane is
+//    only ever touched by one thread, so the scatter is plain load-add-store on shared
+//    memory, with a fixed summation order (bitwise reproducible); the band is written to
+//    HBM once with coalesced stores.  The reference issues 4*R*C*AH*AW global fp32 REDs
+//    (roi_align_kernel.cu:131-134).
+//
+//  * generic kernels for shapes the resident layouts cannot hold (channels % 16 != 0,
+//    planes too large for shared memory, aligned size > 16, no plan): one CTA per
+//    (RoI, channel block), geometry hoisted to shared memory, coalesced output, fp32
+//    atomics in the backward.
 #include "common.cuh"
 
 namespace tlod {
@@ -81,191 +92,298 @@ __global__ void __launch_bounds__(256)
 }
 
 // ===========================================================================
+// plan
+// ===========================================================================
+constexpr int PL_MAXB = 1024;  // images per call on the planned paths
+constexpr int PL_MAXA = 16;    // aligned_h / aligned_w limit on the planned paths
+constexpr int PL_THREADS = 256;
+
+// Column chain of one RoI for the backward pass (aligned_w == 8).  Walking the 8 samples of
+// a row left to right, (a0, a1) accumulate the values of cells (cur, cur + 1):
+//     a0' = g*cw0[t] + ms[t]*a0 + mh[t]*a1        a1' = g*cw1[t] + ms[t]*a1
+// (same cell: ms=1; moved right by one: mh=1; jumped: both 0).  Before sample t (t = 1..7)
+// and after the last one (t = 8) the accumulators that fall out of the window are final:
+// a0 -> cell ex[t] if bit t of en0, a1 -> cell ex[t] + 1 if bit t of en1.  All cells emitted
+// for one row are distinct, so their read-modify-writes are independent.
+struct __align__(16) BwdCols {
+  float cw0[8], cw1[8], ms[8], mh[8];
+  int ex[9];
+  unsigned en0, en1;
+  int all_jump;  // every valid sample starts a new pair of cells: chain is the identity
+};
+static_assert(sizeof(BwdCols) == 176, "BwdCols layout");
+
+struct PlanLayout {
+  size_t cum, list, yrow, tabs, bwdx, total;
+};
+__host__ __device__ inline size_t pl_align(size_t v) { return (v + 255) / 256 * 256; }
+__host__ __device__ inline PlanLayout plan_layout(int B, int R) {
+  PlanLayout L;
+  size_t off = 0;
+  L.cum = off;  off = pl_align(off + (size_t)(B + 2) * 4);
+  L.list = off; off = pl_align(off + (size_t)R * 4);
+  L.yrow = off; off = pl_align(off + (size_t)R * 32);
+  L.tabs = off; off = pl_align(off + (size_t)R * 512);
+  L.bwdx = off; off = pl_align(off + (size_t)R * sizeof(BwdCols));
+  L.total = off;
+  return L;
+}
+
+struct PlanPtrs {
+  int* cum;        // [B + 2] exclusive prefix of RoIs per image; slot B = invalid image index
+  int* list;       // [R] RoI indices sorted by image, stable
+  short* yrow;     // [R][16] first sampled row of each output row, -1 if none
+  float4* tabs;    // [R][32] rows 0..15: {row*W | -1, w0, w1, row}; cols 16..31: {col | -1, w0, w1, -}
+  BwdCols* bwdx;   // [R]
+};
+__host__ __device__ inline PlanPtrs plan_ptrs(void* base, int B, int R) {
+  const PlanLayout L = plan_layout(B, R);
+  unsigned char* p = (unsigned char*)base;
+  PlanPtrs q;
+  q.cum = (int*)(p + L.cum);
+  q.list = (int*)(p + L.list);
+  q.yrow = (short*)(p + L.yrow);
+  q.tabs = (float4*)(p + L.tabs);
+  q.bwdx = (BwdCols*)(p + L.bwdx);
+  return q;
+}
+
+__device__ __forceinline__ int roi_image(const float* __restrict__ rois, int i, int B) {
+  const int b = (int)__ldg(rois + (size_t)i * 5);
+  return (b < 0 || b >= B) ? B : b;
+}
+
+// CTA 0: counting sort of the RoI indices by image (stable).  CTAs >= 1: one warp per RoI
+// computes its 32 table entries and the backward column chain.
+__global__ void __launch_bounds__(PL_THREADS)
+    roi_align_plan_kernel(const float* __restrict__ rois, PlanPtrs pl, int B, int H, int W, int R,
+                          int AH, int AW, float scale) {
+  const int tid = threadIdx.x, lane = lane_id(), wid = warp_id();
+  if (blockIdx.x == 0) {
+    __shared__ int cnt[PL_MAXB + 2];
+    __shared__ int next[PL_MAXB + 2];
+    __shared__ int carry;
+    for (int i = tid; i <= B; i += PL_THREADS) cnt[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < R; i += PL_THREADS) atomicAdd(&cnt[roi_image(rois, i, B)], 1);
+    __syncthreads();
+    if (wid == 0) {
+      int run = 0;
+      for (int base = 0; base <= B; base += 32) {
+        const int i = base + lane;
+        const int v = (i <= B) ? cnt[i] : 0;
+        int incl = v;
+        for (int d = 1; d < 32; d <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += t;
+        }
+        if (i <= B) {
+          next[i] = run + incl - v;
+          pl.cum[i] = run + incl - v;
+        }
+        run += __shfl_sync(0xffffffffu, incl, 31);
+      }
+      if (lane == 0) {
+        pl.cum[B + 1] = run;
+        carry = run;
+      }
+    }
+    __syncthreads();
+    for (int base = 0; base < R; base += PL_THREADS) {
+      const int i = base + tid;
+      const int b = (i < R) ? roi_image(rois, i, B) : -1 - tid;  // unique dummy keys
+      for (int w = 0; w < PL_THREADS / 32; ++w) {
+        if (wid == w) {
+          const unsigned peers = __match_any_sync(0xffffffffu, b);
+          const int leader = __ffs(peers) - 1;
+          int pos = 0;
+          if (lane == leader && b >= 0) {
+            pos = next[b];
+            next[b] = pos + __popc(peers);
+          }
+          pos = __shfl_sync(0xffffffffu, pos, leader);
+          if (b >= 0) pl.list[pos + __popc(peers & ((1u << lane) - 1u))] = i;
+        }
+        __syncthreads();
+      }
+    }
+    return;
+  }
+
+  const int n = (blockIdx.x - 1) * (PL_THREADS / 32) + wid;
+  if (n >= R) return;
+  const float* r = rois + (size_t)n * 5;
+  AxisTab t;
+  int start = -1;
+  t.off = -1; t.w0 = 0.f; t.w1 = 0.f;
+  if (lane < 16) {
+    if (lane < AH) {
+      const AlignAxis a = align_axis(__ldg(r + 2), __ldg(r + 4), scale, AH, H, lane);
+      t = make_tab(a, W);
+      start = a.valid ? a.start : -1;
+    }
+    pl.yrow[(size_t)n * 16 + lane] = (short)start;
+  } else if (lane - 16 < AW) {
+    const AlignAxis a = align_axis(__ldg(r + 1), __ldg(r + 3), scale, AW, W, lane - 16);
+    t = make_tab(a, 1);
+    start = a.valid ? a.start : -1;
+  }
+  // invalid samples carry zero weights so that the kernels need no select
+  if (t.off < 0) { t.w0 = 0.f; t.w1 = 0.f; }
+  pl.tabs[(size_t)n * 32 + lane] = make_float4(__int_as_float(t.off), t.w0, t.w1, __int_as_float(start));
+
+  if (AW == 8) {
+    // every lane walks the chain (cheap); lane t keeps the entries of sample t
+    int cur = -1;
+    unsigned en0 = 0u, en1 = 0u;
+    int all_jump = 1;
+    float my_cw0 = 0.f, my_cw1 = 0.f, my_ms = 1.f, my_mh = 0.f;
+    int my_ex = 0, ex8 = 0;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      const int x = __shfl_sync(0xffffffffu, t.off, 16 + s);
+      const float w0 = __shfl_sync(0xffffffffu, t.w0, 16 + s);
+      const float w1 = __shfl_sync(0xffffffffu, t.w1, 16 + s);
+      float ms = 1.f, mh = 0.f;
+      const int ex = cur < 0 ? 0 : cur;
+      if (x >= 0) {
+        if (cur < 0) {
+          ms = 0.f;
+        } else if (x == cur) {
+          all_jump = 0;
+        } else if (x == cur + 1) {
+          ms = 0.f; mh = 1.f;
+          en0 |= 1u << s;
+          all_jump = 0;
+        } else {
+          ms = 0.f;
+          en0 |= 1u << s;
+          en1 |= 1u << s;
+        }
+        cur = x;
+      } else {
+        all_jump = 0;  // the fast path assumes sample t's cells are emitted at transition t+1
+      }
+      if (lane == s) { my_cw0 = w0; my_cw1 = w1; my_ms = ms; my_mh = mh; my_ex = ex; }
+    }
+    if (cur >= 0) { en0 |= 1u << 8; en1 |= 1u << 8; ex8 = cur; }
+    BwdCols* bc = pl.bwdx + n;
+    if (lane < 8) {
+      bc->cw0[lane] = my_cw0; bc->cw1[lane] = my_cw1; bc->ms[lane] = my_ms; bc->mh[lane] = my_mh;
+      bc->ex[lane] = my_ex;
+    } else if (lane == 8) {
+      bc->ex[8] = ex8; bc->en0 = en0; bc->en1 = en1; bc->all_jump = all_jump;
+    }
+  }
+}
+
+// ===========================================================================
 // plane-resident forward
 // ===========================================================================
 constexpr int PR_CH = 16;        // channels per slab == warps per CTA
 constexpr int PR_THREADS = 512;  // 16 warps
-constexpr int PR_LIST = 1024;    // RoI indices staged per refill
-constexpr int PR_MAXB = 1024;    // images per call on this path
-constexpr int PR_MAXA = 16;      // aligned_h / aligned_w limit on this path
 
 struct PRShared {
-  int cnt[PR_MAXB + 2];  // RoIs per image (+1 slot: RoIs with an invalid image index)
-  int cum[PR_MAXB + 2];  // exclusive prefix of cnt
-  int list[PR_LIST];     // RoI indices of the current (image, rank range)
-  int warp_sums[PR_THREADS / 32];
-  int cur[4];            // broadcast slots: image, slab, rank_lo, rank_hi
-  AxisTab rows[PR_THREADS / 32][PR_MAXA];
-  AxisTab cols[PR_THREADS / 32][PR_MAXA];
+  float4 wtab[PR_THREADS / 32][32];  // per-warp copy of the current RoI's tables
+  int cur[4];                        // broadcast slots: image, slab, rank_lo, rank_hi
 };
 
-__host__ __device__ inline int pr_plane_stride(int hw) {
-  int p = hw;
-  while ((p & 3) != 2) ++p;  // 2 (mod 4): 16 channels -> 16 distinct same-parity banks
+// Shared-memory plane geometry: rows padded to an even stride, planes to 2 (mod 4) floats.
+// Then (i) the 16 channels of a slab start on 16 distinct banks of one parity and (ii) every
+// row starts on an even word, so a lane that reads column x and a lane that reads column
+// x + 1 -- of any two rows -- are always on banks of opposite parity.
+__host__ __device__ inline int pr_row_stride(int w) { return w + (w & 1); }
+__host__ __device__ inline int pr_plane_stride(int h, int w) {
+  int p = h * pr_row_stride(w);
+  while ((p & 3) != 2) ++p;
   return p;
 }
 
-// Exclusive prefix over cnt[0..nb) by warp 0; cum[nb] = total.
-__device__ inline void pr_prefix(PRShared& sh, int nb) {
-  if (warp_id() == 0) {
-    int carry = 0;
-    for (int base = 0; base < nb; base += 32) {
-      int i = base + lane_id();
-      int v = (i < nb) ? sh.cnt[i] : 0;
-      int incl = v;
-      for (int d = 1; d < 32; d <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane_id() >= d) incl += t;
-      }
-      if (i < nb) sh.cum[i] = carry + incl - v;
-      carry += __shfl_sync(0xffffffffu, incl, 31);
-    }
-    if (lane_id() == 0) sh.cum[nb] = carry;
-  }
-}
-
-// Fill sh.list with the indices of the RoIs of image `img` whose rank (position
-// among that image's RoIs in index order) lies in [lo, hi), hi - lo <= PR_LIST.
-__device__ inline void pr_build_list(PRShared& sh, const float* __restrict__ rois, int R, int B,
-                                     int img, int lo, int hi) {
-  int running = 0;
-  for (int base = 0; base < R && running < hi; base += PR_THREADS) {
-    const int i = base + threadIdx.x;
-    bool m = false;
-    if (i < R) {
-      int b = (int)__ldg(rois + (size_t)i * 5);
-      if (b < 0 || b >= B) b = B;
-      m = (b == img);
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, m);
-    if (lane_id() == 0) sh.warp_sums[warp_id()] = __popc(bal);
-    __syncthreads();
-    int before = running;
-    int total = 0;
-#pragma unroll
-    for (int w = 0; w < PR_THREADS / 32; ++w) {
-      const int s = sh.warp_sums[w];
-      if (w < warp_id()) before += s;
-      total += s;
-    }
-    if (m) {
-      const int rank = before + __popc(bal & ((1u << lane_id()) - 1u));
-      if (rank >= lo && rank < hi) sh.list[rank - lo] = i;
-    }
-    running += total;
-    __syncthreads();
-  }
-}
-
-__device__ __forceinline__ void st_global_v4(float* p, float a, float b, float c, float d) {
-  asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
+__device__ __forceinline__ void st_global_v8(float* p, const float (&o)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(o[0]),
+               "f"(o[1]), "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7])
                : "memory");
 }
 
-// One warp, one RoI, 16 channels, AW == 8 and AH even: lane (c, slot) produces the
-// full 8-wide output row ph = 2*j + slot of channel c (32 contiguous bytes).
-__device__ __forceinline__ void pr_fwd_roi_fast8(const float* __restrict__ planes, int Pp, int W,
-                                                 const AxisTab* rows, const AxisTab* cols, int AH,
-                                                 float* __restrict__ out_roi /* (16, AH, 8) */) {
-  const int lane = lane_id();
-  const int c = lane >> 1, slot = lane & 1;
-  const float* plane = planes + c * Pp;
-  int cx[8];
-  float cw0[8], cw1[8];
+// One warp, one RoI, 16 channels, AW == 8: lane (c, slot) produces the whole 8-wide output
+// rows ph = 2j + slot of channel c and writes each with one 256-bit store (a lane pair
+// covers 64 contiguous bytes).  Slot 0 reads its cell pairs as (x, x+1), slot 1 as (x+1, x):
+// with the even row stride that alone makes every gather bank-conflict free.
+__device__ __forceinline__ void pr_fwd_roi_w8(const float* __restrict__ plane, int Wp,
+                                              const float4* __restrict__ wtab, int AH, int slot,
+                                              float* __restrict__ out_c /* channel c of the RoI */) {
+  int xa[8], xb[8];
+  float wp[8], wq[8];
 #pragma unroll
-  for (int pw = 0; pw < 8; ++pw) {
-    const AxisTab t = cols[pw];
-    cx[pw] = t.off;
-    cw0[pw] = t.w0;
-    cw1[pw] = t.w1;
+  for (int q = 0; q < 8; ++q) {
+    const float4 m = wtab[16 + q];
+    int x = __float_as_int(m.x);
+    x = x < 0 ? 0 : x;
+    xa[q] = x + slot;
+    xb[q] = x + (slot ^ 1);
+    wp[q] = slot ? m.z : m.y;
+    wq[q] = slot ? m.y : m.z;
   }
-  for (int j = 0; j < AH / 2; ++j) {
-    const int ph = 2 * j + slot;
-    const AxisTab row = rows[ph];
-    const int roff = row.off < 0 ? 0 : row.off;
-    const int other = __shfl_xor_sync(0xffffffffu, roff, 1);
-    // slot 1 reads (x+1, x) instead of (x, x+1) when both rows start on the same
-    // parity, so that the two half-warps always hit opposite bank parities.
-    const int flip = slot & (((roff ^ other) & 1) ^ 1);
+  for (int j = 0; 2 * j < AH; ++j) {
+    const int ph = min(2 * j + slot, AH - 1);
+    const float4 r = wtab[ph];
+    const float* b0 = plane + __float_as_int(r.x);
+    const float* b1 = b0 + Wp;
     float o[8];
 #pragma unroll
-    for (int pw = 0; pw < 8; ++pw) {
-      const int x = cx[pw] < 0 ? 0 : cx[pw];
-      const float* p = plane + roff + x;
-      const float a = p[flip];
-      const float b = p[flip ^ 1];
-      const float cc = p[W + flip];
-      const float d = p[W + (flip ^ 1)];
-      const float wa = flip ? cw1[pw] : cw0[pw];
-      const float wb = flip ? cw0[pw] : cw1[pw];
-      float v = a * (row.w0 * wa);
-      v = fmaf(b, row.w0 * wb, v);
-      v = fmaf(cc, row.w1 * wa, v);
-      v = fmaf(d, row.w1 * wb, v);
-      o[pw] = (row.off < 0 || cx[pw] < 0) ? 0.f : v;
+    for (int q = 0; q < 8; ++q) {
+      const float p00 = b0[xa[q]], p01 = b0[xb[q]];
+      const float p10 = b1[xa[q]], p11 = b1[xb[q]];
+      const float t0 = fmaf(p01, wq[q], p00 * wp[q]);
+      const float t1 = fmaf(p11, wq[q], p10 * wp[q]);
+      o[q] = fmaf(t1, r.z, t0 * r.y);
     }
-    float* dst = out_roi + ((size_t)c * AH + ph) * 8;
-    st_global_v4(dst, o[0], o[1], o[2], o[3]);
-    st_global_v4(dst + 4, o[4], o[5], o[6], o[7]);
+    if (2 * j + slot < AH) st_global_v8(out_c + ph * 8, o);
   }
 }
 
 // Any AH, AW <= 16: lane (c, slot) produces samples i = 2k + slot of channel c.
-__device__ __forceinline__ void pr_fwd_roi_any(const float* __restrict__ planes, int Pp, int W,
-                                               const AxisTab* rows, const AxisTab* cols, int AH,
-                                               int AW, float* __restrict__ out_roi) {
-  const int lane = lane_id();
-  const int c = lane >> 1, slot = lane & 1;
-  const float* plane = planes + c * Pp;
+__device__ __forceinline__ void pr_fwd_roi_any(const float* __restrict__ plane, int Wp,
+                                               const float4* __restrict__ wtab, int AH, int AW,
+                                               int slot, float* __restrict__ out_c) {
   const int S = AH * AW;
   for (int k = 0; 2 * k < S; ++k) {
     const int i = min(2 * k + slot, S - 1);
     const int ph = i / AW, pw = i - ph * AW;
-    const AxisTab row = rows[ph], col = cols[pw];
-    const bool ok = row.off >= 0 && col.off >= 0;
-    const int off = ok ? row.off + col.off : 0;
+    const float4 row = wtab[ph], col = wtab[16 + pw];
+    const int co = __float_as_int(col.x);
+    const int off = __float_as_int(row.x) + (co < 0 ? 0 : co);
     const int other = __shfl_xor_sync(0xffffffffu, off, 1);
     const int flip = slot & (((off ^ other) & 1) ^ 1);
     const float* p = plane + off;
     const float a = p[flip];
     const float b = p[flip ^ 1];
-    const float cc = p[W + flip];
-    const float d = p[W + (flip ^ 1)];
-    const float wa = flip ? col.w1 : col.w0;
-    const float wb = flip ? col.w0 : col.w1;
-    float v = a * (row.w0 * wa);
-    v = fmaf(b, row.w0 * wb, v);
-    v = fmaf(cc, row.w1 * wa, v);
-    v = fmaf(d, row.w1 * wb, v);
-    if (2 * k + slot < S) out_roi[(size_t)c * S + i] = ok ? v : 0.f;
+    const float cc = p[Wp + flip];
+    const float d = p[Wp + (flip ^ 1)];
+    const float wa = flip ? col.z : col.y;
+    const float wb = flip ? col.y : col.z;
+    const float t0 = fmaf(b, wb, a * wa);
+    const float t1 = fmaf(d, wb, cc * wa);
+    if (2 * k + slot < S) out_c[i] = fmaf(t1, row.z, t0 * row.y);
   }
 }
 
-template <bool FAST8>
+template <bool W8>
 __global__ void __launch_bounds__(PR_THREADS, 1)
-    roi_align_fwd_planes_kernel(const float* __restrict__ features, const float* __restrict__ rois,
-                                float* __restrict__ output, int B, int C, int H, int W, int R,
-                                int AH, int AW, float scale, int Pp) {
+    roi_align_fwd_planes_kernel(const float* __restrict__ features, float* __restrict__ output,
+                                PlanPtrs pl, int B, int C, int H, int W, int R, int AH, int AW,
+                                int Pp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* planes = reinterpret_cast<float*>(smem_raw);
   PRShared& sh = *reinterpret_cast<PRShared*>(smem_raw + (size_t)PR_CH * Pp * sizeof(float));
   const int tid = threadIdx.x, lane = lane_id(), wid = warp_id();
   const int nslabs = C / PR_CH;
   const int P = H * W, S = AH * AW;
+  const int Wp = pr_row_stride(W);
+  const int c = lane >> 1, slot = lane & 1;
+  const int* __restrict__ cum = pl.cum;
 
-  // ---- RoIs per image (slot B collects RoIs with an invalid image index) ----
-  for (int i = tid; i <= B; i += PR_THREADS) sh.cnt[i] = 0;
-  __syncthreads();
-  for (int i = tid; i < R; i += PR_THREADS) {
-    int b = (int)__ldg(rois + (size_t)i * 5);
-    if (b < 0 || b >= B) b = B;
-    atomicAdd(&sh.cnt[b], 1);
-  }
-  __syncthreads();
-  pr_prefix(sh, B + 1);
-  __syncthreads();
-
-  // ---- this CTA's contiguous range of (image, slab, RoI-rank) units ----
+  // this CTA's contiguous range of (image, slab, RoI-rank) units
   const long long U = (long long)nslabs * R;
   long long u = U * blockIdx.x / gridDim.x;
   const long long u_end = U * (blockIdx.x + 1) / gridDim.x;
@@ -274,18 +392,18 @@ __global__ void __launch_bounds__(PR_THREADS, 1)
   while (u < u_end) {
     if (tid == 0) {
       // image b with nslabs*cum[b] <= u < nslabs*cum[b+1]
-      int lo = 0, hi = B;  // invariant: answer in [lo, hi]
+      int lo = 0, hi = B;
       while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
-        if ((long long)nslabs * sh.cum[mid] <= u) lo = mid; else hi = mid - 1;
+        if ((long long)nslabs * __ldg(cum + mid) <= u) lo = mid; else hi = mid - 1;
       }
-      // skip images without RoIs (cum[b] == cum[b+1])
-      while (lo < B && sh.cnt[lo] == 0) ++lo;
-      const long long rem = u - (long long)nslabs * sh.cum[lo];
-      const int slab = (int)(rem / sh.cnt[lo]);
-      const int r_lo = (int)(rem - (long long)slab * sh.cnt[lo]);
-      long long room = u_end - u;
-      int r_hi = sh.cnt[lo];
+      while (lo < B && __ldg(cum + lo + 1) == __ldg(cum + lo)) ++lo;  // images without RoIs
+      const int cnt = __ldg(cum + lo + 1) - __ldg(cum + lo);
+      const long long rem = u - (long long)nslabs * __ldg(cum + lo);
+      const int slab = (int)(rem / cnt);
+      const int r_lo = (int)(rem - (long long)slab * cnt);
+      const long long room = u_end - u;
+      int r_hi = cnt;
       if (room < (long long)(r_hi - r_lo)) r_hi = r_lo + (int)room;
       sh.cur[0] = lo; sh.cur[1] = slab; sh.cur[2] = r_lo; sh.cur[3] = r_hi;
     }
@@ -293,242 +411,273 @@ __global__ void __launch_bounds__(PR_THREADS, 1)
     const int img = sh.cur[0], slab = sh.cur[1], r_lo = sh.cur[2], r_hi = sh.cur[3];
     const int c0 = slab * PR_CH;
 
-    // ---- stage the 16 planes of (img, slab): warp w copies channel w ----
+    // ---- stage the 16 planes of (img, slab): warp w copies channel w, 32 loads in flight ----
     if (img < B && (img != staged_img || slab != staged_slab)) {
       const float* g = features + ((size_t)img * C + c0 + wid) * P;
       float* s = planes + wid * Pp;
-      int i = lane;
-      for (; i + 7 * 32 < P; i += 8 * 32) {
-        float v[8];
+      const int pad = Wp - W;
+      int y = lane / W, x = lane - y * W;  // position of element i = lane + 32 k
+      for (int i = lane; i < P; i += 32 * 32) {
+        float v[32];
+        int d[32];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = __ldg(g + i + k * 32);
+        for (int k = 0; k < 32; ++k) {
+          v[k] = (i + k * 32 < P) ? __ldg(g + i + k * 32) : 0.f;
+          d[k] = i + k * 32 + y * pad;
+          x += 32;
+          while (x >= W) { x -= W; ++y; }
+        }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) s[i + k * 32] = v[k];
+        for (int k = 0; k < 32; ++k)
+          if (i + k * 32 < P) s[d[k]] = v[k];
       }
-      for (; i < P; i += 32) s[i] = __ldg(g + i);
       staged_img = img;
       staged_slab = slab;
     }
+    __syncthreads();
 
-    for (int base = r_lo; base < r_hi; base += PR_LIST) {
-      const int top = min(r_hi, base + PR_LIST);
-      pr_build_list(sh, rois, R, B, img, base, top);  // ends with __syncthreads()
-      for (int e = wid; e < top - base; e += PR_THREADS / 32) {
-        const int n = sh.list[e];
-        float* out_roi = output + ((size_t)n * C + c0) * S;
-        if (img == B) {  // invalid image index: zeros
-          for (int i = lane; i < PR_CH * S; i += 32) out_roi[i] = 0.f;
-          continue;
+    const int base = __ldg(cum + img);
+    const float* plane = planes + c * Pp;
+    float4* wtab = sh.wtab[wid];
+    int e = r_lo + wid;
+    int n = (e < r_hi) ? __ldg(pl.list + base + e) : 0;
+    float4 t = (e < r_hi && img < B) ? __ldg(pl.tabs + (size_t)n * 32 + lane) : make_float4(0, 0, 0, 0);
+    for (; e < r_hi; e += PR_THREADS / 32) {
+      // prefetch the next RoI of this warp
+      const int e2 = e + PR_THREADS / 32;
+      const int n2 = (e2 < r_hi) ? __ldg(pl.list + base + e2) : 0;
+      float4 t2 = make_float4(0, 0, 0, 0);
+      if (e2 < r_hi && img < B) t2 = __ldg(pl.tabs + (size_t)n2 * 32 + lane);
+
+      float* out_roi = output + ((size_t)n * C + c0) * S;
+      if (img == B) {  // invalid image index: zeros
+        for (int i = lane; i < PR_CH * S; i += 32) out_roi[i] = 0.f;
+      } else {
+        // rows: cell offset of the first sampled row in the padded plane (0 if out of range:
+        // the weights are zero then)
+        if (lane < 16) {
+          const int start = __float_as_int(t.w);
+          t.x = __int_as_float(start < 0 ? 0 : start * Wp);
         }
-        const float* r = rois + (size_t)n * 5;
-        if (lane < AH)
-          sh.rows[wid][lane] = make_tab(align_axis(__ldg(r + 2), __ldg(r + 4), scale, AH, H, lane), W);
-        else if (lane >= 16 && lane < 16 + AW)
-          sh.cols[wid][lane - 16] =
-              make_tab(align_axis(__ldg(r + 1), __ldg(r + 3), scale, AW, W, lane - 16), 1);
+        wtab[lane] = t;
         __syncwarp();
-        if (FAST8)
-          pr_fwd_roi_fast8(planes, Pp, W, sh.rows[wid], sh.cols[wid], AH, out_roi);
+        if (W8)
+          pr_fwd_roi_w8(plane, Wp, wtab, AH, slot, out_roi + (size_t)c * S);
         else
-          pr_fwd_roi_any(planes, Pp, W, sh.rows[wid], sh.cols[wid], AH, AW, out_roi);
+          pr_fwd_roi_any(plane, Wp, wtab, AH, AW, slot, out_roi + (size_t)c * S);
         __syncwarp();
       }
-      __syncthreads();
+      n = n2;
+      t = t2;
     }
+    __syncthreads();
     u += (r_hi - r_lo);
   }
 }
 
 // ===========================================================================
-// plane-resident backward (no atomics)
+// band-resident backward (no atomics)
 // ===========================================================================
-// One CTA owns the gradient planes of (image, 16-channel slab, row band) exclusively: they
-// are accumulated in shared memory and written to HBM once with plain coalesced stores, so
-// bottom_grad needs neither a memset nor a single atomic (the reference issues
-// 4 * R * C * AH * AW global fp32 REDs, roi_align_kernel.cu:131-134).
-//
-// Inside the CTA the 16 warps never touch the same cell: warp w owns the plane rows
-// y == w (mod 16) of the band.  A RoI contributes 2*AH "row entries" (ph, dy) -> row
-// hs[ph] + dy; each entry is scattered by the one warp that owns that row, lane =
-// 2*channel + slot, slot = half of the 8 samples of the row.  As in the forward the plane
-// stride is 2 (mod 4) and the two slots update cells of opposite column parity, so every
-// read-modify-write instruction is bank-conflict free.  The order of additions into a cell
-// is fixed (RoI index, then ph, dy, pw), so the result is bitwise reproducible.
-//
-// The (16, AH, 8) gradient tiles of the next PB_NB RoIs are fetched with cp.async into a
-// second shared-memory stage while the current batch is scattered.
-constexpr int PB_NB = 4;      // RoIs per batch (stage)
-constexpr int PB_LIST = 512;  // RoI indices per refill
+constexpr int BW_WARPS = 4;
+constexpr int BW_THREADS = BW_WARPS * 32;
+constexpr int BW_CH = BW_WARPS * 32;  // channels per CTA
+constexpr int BW_CHUNK = BW_THREADS;  // RoIs examined per round
 
-struct PBShared {
-  int list[PB_LIST];
-  int warp_sums[PR_THREADS / 32];
-  AxisTab rows[2][PB_NB][PR_MAXA];  // off = first row index (not scaled) or -1
-  AxisTab cols[2][PB_NB][PR_MAXA];
+struct BWShared {
+  int items[BW_CHUNK * 16];  // (roi << 4) | ph, in (list order, ph) order
+  int warp_sums[BW_WARPS];
+  int nitems;
 };
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+__device__ __forceinline__ void ldg_row8(const float* __restrict__ p, float (&g)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w;
+  g[4] = b.x; g[5] = b.y; g[6] = b.z; g[7] = b.w;
 }
 
-// RoIs of image `img` whose sampled rows can intersect [y_lo, y_hi), ranks [lo, hi) -> list
-__device__ inline int pb_build_list(PBShared& sh, const float* __restrict__ rois, int R, int img,
-                                    int AH, int H, float scale, int y_lo, int y_hi, int lo, int hi) {
-  int running = 0;
-  for (int base = 0; base < R; base += PR_THREADS) {
-    const int i = base + threadIdx.x;
-    bool m = false;
-    if (i < R) {
-      const float* r = rois + (size_t)i * 5;
-      if ((int)__ldg(r) == img) {
-        const AlignAxis a0 = align_axis(__ldg(r + 2), __ldg(r + 4), scale, AH, H, 0);
-        const AlignAxis a1 = align_axis(__ldg(r + 2), __ldg(r + 4), scale, AH, H, AH - 1);
-        m = (a0.start < y_hi) && (a1.start + 1 >= y_lo);
-      }
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, m);
-    if (lane_id() == 0) sh.warp_sums[warp_id()] = __popc(bal);
-    __syncthreads();
-    int before = running, total = 0;
+struct BwdState {
+  float cw0[8], cw1[8], ms[8], mh[8];
+  int ex[9];
+  unsigned en0, en1;
+  int all_jump;
+  int n;
+};
+
+__device__ __forceinline__ void bw_load_cols(BwdState& s, const BwdCols* __restrict__ bc) {
+  const float4* q = reinterpret_cast<const float4*>(bc);
+  float4 v[11];
 #pragma unroll
-    for (int w = 0; w < PR_THREADS / 32; ++w) {
-      const int v = sh.warp_sums[w];
-      if (w < warp_id()) before += v;
-      total += v;
-    }
-    if (m) {
-      const int rank = before + __popc(bal & ((1u << lane_id()) - 1u));
-      if (rank >= lo && rank < hi) sh.list[rank - lo] = i;
-    }
-    running += total;
-    __syncthreads();
+  for (int i = 0; i < 11; ++i) v[i] = __ldg(q + i);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    s.cw0[4 * i] = v[i].x; s.cw0[4 * i + 1] = v[i].y; s.cw0[4 * i + 2] = v[i].z; s.cw0[4 * i + 3] = v[i].w;
+    s.cw1[4 * i] = v[2 + i].x; s.cw1[4 * i + 1] = v[2 + i].y; s.cw1[4 * i + 2] = v[2 + i].z; s.cw1[4 * i + 3] = v[2 + i].w;
+    s.ms[4 * i] = v[4 + i].x; s.ms[4 * i + 1] = v[4 + i].y; s.ms[4 * i + 2] = v[4 + i].z; s.ms[4 * i + 3] = v[4 + i].w;
+    s.mh[4 * i] = v[6 + i].x; s.mh[4 * i + 1] = v[6 + i].y; s.mh[4 * i + 2] = v[6 + i].z; s.mh[4 * i + 3] = v[6 + i].w;
   }
-  return running;  // number of matching RoIs in the whole array
+  s.ex[0] = __float_as_int(v[8].x); s.ex[1] = __float_as_int(v[8].y);
+  s.ex[2] = __float_as_int(v[8].z); s.ex[3] = __float_as_int(v[8].w);
+  s.ex[4] = __float_as_int(v[9].x); s.ex[5] = __float_as_int(v[9].y);
+  s.ex[6] = __float_as_int(v[9].z); s.ex[7] = __float_as_int(v[9].w);
+  s.ex[8] = __float_as_int(v[10].x);
+  s.en0 = (unsigned)__float_as_int(v[10].y);
+  s.en1 = (unsigned)__float_as_int(v[10].z);
+  s.all_jump = __float_as_int(v[10].w);
 }
 
-__global__ void __launch_bounds__(PR_THREADS, 1)
-    roi_align_bwd_planes_kernel(const float* __restrict__ top_grad, const float* __restrict__ rois,
-                                float* __restrict__ bottom_grad, int B, int C, int H, int W, int R,
-                                int AH, float scale, int nsplit, int band_rows, int Ppb, int TS) {
+// Add rw * (emitted cell values) into one plane row.  All enabled cells are distinct, so
+// the loads are issued together, then the stores.
+__device__ __forceinline__ void bw_rmw_row(float* __restrict__ row, float rw, const BwdState& s,
+                                           const float (&e0)[9], const float (&e1)[9]) {
+  float o0[9], o1[9];
+#pragma unroll
+  for (int t = 1; t <= 8; ++t) {
+    o0[t] = ((s.en0 >> t) & 1u) ? row[s.ex[t]] : 0.f;
+    o1[t] = ((s.en1 >> t) & 1u) ? row[s.ex[t] + 1] : 0.f;
+  }
+#pragma unroll
+  for (int t = 1; t <= 8; ++t) {
+    if ((s.en0 >> t) & 1u) row[s.ex[t]] = fmaf(rw, e0[t], o0[t]);
+    if ((s.en1 >> t) & 1u) row[s.ex[t] + 1] = fmaf(rw, e1[t], o1[t]);
+  }
+}
+
+__device__ __forceinline__ void bw_item(float* __restrict__ plane, int W, int y_lo, int y_hi,
+                                        const float (&g)[8], const float4 rowt, const BwdState& s) {
+  float e0[9], e1[9];
+  if (s.all_jump) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      e0[t + 1] = g[t] * s.cw0[t];
+      e1[t + 1] = g[t] * s.cw1[t];
+    }
+  } else {
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      if (t > 0) { e0[t] = a0; e1[t] = a1; }
+      const float na0 = fmaf(s.ms[t], a0, fmaf(s.mh[t], a1, g[t] * s.cw0[t]));
+      a1 = fmaf(s.ms[t], a1, g[t] * s.cw1[t]);
+      a0 = na0;
+    }
+    e0[8] = a0; e1[8] = a1;
+  }
+  const int y0 = __float_as_int(rowt.w);
+  if (y0 >= y_lo && y0 < y_hi) bw_rmw_row(plane + (y0 - y_lo) * W, rowt.y, s, e0, e1);
+  if (y0 + 1 >= y_lo && y0 + 1 < y_hi) bw_rmw_row(plane + (y0 + 1 - y_lo) * W, rowt.z, s, e0, e1);
+}
+
+__global__ void __launch_bounds__(BW_THREADS)
+    roi_align_bwd_planes_kernel(const float* __restrict__ top_grad, float* __restrict__ bottom_grad,
+                                PlanPtrs pl, int B, int C, int H, int W, int AH, int ngroups,
+                                int nbands, int band_rows, int Sb) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* planes = reinterpret_cast<float*>(smem_raw);
-  float* tiles = planes + (size_t)PR_CH * Ppb;                       // [2][PB_NB][16 * TS]
-  PBShared& sh = *reinterpret_cast<PBShared*>(tiles + 2 * PB_NB * PR_CH * TS);
+  BWShared& sh = *reinterpret_cast<BWShared*>(smem_raw + (size_t)BW_CH * Sb * sizeof(float));
   const int tid = threadIdx.x, lane = lane_id(), wid = warp_id();
-  const int nslabs = C / PR_CH;
-  const int band = blockIdx.x % nsplit;
-  const int pair = blockIdx.x / nsplit;
-  const int img = pair / nslabs, c0 = (pair % nslabs) * PR_CH;
+  const int band = blockIdx.x % nbands;
+  const int rest = blockIdx.x / nbands;
+  const int grp = rest % ngroups, img = rest / ngroups;
   const int y_lo = band * band_rows, y_hi = min(H, y_lo + band_rows);
-  const int S = AH * 8, S4 = S / 4;
-  const int tile_floats = PR_CH * TS;
+  const int cw = grp * BW_CH + wid * 32;  // first channel of this warp
+  const bool active = cw < C;             // C % 32 == 0
+  const int c = cw + lane;
+  float* plane = planes + (size_t)(wid * 32 + lane) * Sb;
 
-  for (int i = tid; i < PR_CH * Ppb; i += PR_THREADS) planes[i] = 0.f;
+  for (int i = tid; i < BW_CH * Sb; i += BW_THREADS) planes[i] = 0.f;
 
-  const int c = lane >> 1, slot = lane & 1;
-  int done = 0, total = 1;
-  while (done < total) {
-    total = pb_build_list(sh, rois, R, img, AH, H, scale, y_lo, y_hi, done, done + PB_LIST);
-    const int cnt = min(PB_LIST, total - done);  // list entries valid this round
-    const int nbatch = (cnt + PB_NB - 1) / PB_NB;
+  const int base = __ldg(pl.cum + img);
+  const int n_img = __ldg(pl.cum + img + 1) - base;
+  const int S = AH * 8;
+  BwdState st;
+  st.n = -1;
 
-    auto issue = [&](int k) {  // gradient tiles of batch k -> stage k & 1
-      const int nb = min(PB_NB, cnt - k * PB_NB);
-      float* stage = tiles + (size_t)(k & 1) * PB_NB * tile_floats;
-      for (int q = tid; q < nb * PR_CH * S4; q += PR_THREADS) {
-        const int j = q / (PR_CH * S4);
-        const int rem = q - j * (PR_CH * S4);
-        const int ch = rem / S4, f = rem - ch * S4;
-        const int n = sh.list[k * PB_NB + j];
-        cp_async16(stage + j * tile_floats + ch * TS + f * 4,
-                   top_grad + ((size_t)n * C + c0 + ch) * S + f * 4);
-      }
-      cp_async_commit();
-    };
-
-    if (nbatch > 0) issue(0);
-    for (int k = 0; k < nbatch; ++k) {
-      const int nb = min(PB_NB, cnt - k * PB_NB);
-      if (k + 1 < nbatch) issue(k + 1);
-      // sampling tables of batch k
-      if (tid < nb * 32) {
-        const int j = tid >> 5, e = tid & 31;
-        const float* r = rois + (size_t)sh.list[k * PB_NB + j] * 5;
-        if (e < AH) {
-          const AlignAxis a = align_axis(__ldg(r + 2), __ldg(r + 4), scale, AH, H, e);
-          AxisTab t = make_tab(a, 1);
-          sh.rows[k & 1][j][e] = t;
-        } else if (e >= 16 && e < 24) {
-          sh.cols[k & 1][j][e - 16] = make_tab(align_axis(__ldg(r + 1), __ldg(r + 3), scale, 8, W, e - 16), 1);
-        }
-      }
-      if (k + 1 < nbatch) cp_async_wait<1>(); else cp_async_wait<0>();
-      __syncthreads();
-
-      const float* stage = tiles + (size_t)(k & 1) * PB_NB * tile_floats;
-      for (int j = 0; j < nb; ++j) {
-        const AxisTab* rows = sh.rows[k & 1][j];
-        const AxisTab* cols = sh.cols[k & 1][j];
-        // which of the 2*AH row entries (ph = lane >> 1, dy = lane & 1) does this warp own?
-        bool own = false;
-        if ((lane >> 1) < AH) {
-          const int r0 = rows[lane >> 1].off;
-          const int y = r0 + (lane & 1);
-          own = r0 >= 0 && y >= y_lo && y < y_hi && ((y - y_lo) & 15) == wid;
-        }
-        unsigned mine = __ballot_sync(0xffffffffu, own);
-        if (!mine) continue;
-        int cx[4], flip[4];
-        float cw0[4], cw1[4];
+  for (int chunk = 0; chunk < n_img; chunk += BW_CHUNK) {
+    // ---- items of this chunk: (RoI, ph) whose rows y0 / y0+1 intersect the band ----
+    unsigned mask = 0u;
+    int n = 0;
+    if (chunk + tid < n_img) {
+      n = __ldg(pl.list + base + chunk + tid);
+      const int4* yr = reinterpret_cast<const int4*>(pl.yrow + (size_t)n * 16);
+      const int4 a = __ldg(yr), b = __ldg(yr + 1);
+      const int w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const AxisTab t = cols[4 * slot + q];
-          const int xp = cols[4 * (slot ^ 1) + q].off;
-          cx[q] = t.off;
-          cw0[q] = t.w0;
-          cw1[q] = t.w1;
-          // slot 1 swaps its (x, x+1) order when both slots start on the same parity
-          flip[q] = slot & (((t.off ^ xp) & 1) ^ 1);
-        }
-        const float* g_roi = stage + j * tile_floats + c * TS + 4 * slot;
-        while (mine) {
-          const int e = __ffs(mine) - 1;
-          mine &= mine - 1u;
-          const int ph = e >> 1, dy = e & 1;
-          const AxisTab rt = rows[ph];
-          const float rw = dy ? rt.w1 : rt.w0;
-          float* prow = planes + c * Ppb + (rt.off + dy - y_lo) * W;
-          const float4 g = *reinterpret_cast<const float4*>(g_roi + ph * 8);
-          const float gv[4] = {g.x, g.y, g.z, g.w};
+      for (int k = 0; k < 16; ++k) {
+        const int ys = (int)(short)((k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xffff));
+        if (ys >= 0 && ys + 1 >= y_lo && ys < y_hi) mask |= 1u << k;
+      }
+    }
+    const int cnt = __popc(mask);
+    int incl = cnt;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float mv = rw * gv[q];
-            const int x = cx[q], f = flip[q];
-            if (x >= 0) prow[x + f] += mv * (f ? cw1[q] : cw0[q]);
-            __syncwarp();
-            if (x >= 0) prow[x + (f ^ 1)] += mv * (f ? cw0[q] : cw1[q]);
-            __syncwarp();
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) sh.warp_sums[wid] = incl;
+    __syncthreads();  // also orders the previous round's item reads before this round's writes
+    int pos = incl - cnt;
+#pragma unroll
+    for (int w = 0; w < BW_WARPS; ++w)
+      if (w < wid) pos += sh.warp_sums[w];
+    if (tid == BW_THREADS - 1) sh.nitems = pos + cnt;
+    while (mask) {
+      const int k = __ffs(mask) - 1;
+      mask &= mask - 1u;
+      sh.items[pos++] = (n << 4) | k;
+    }
+    __syncthreads();
+    const int nitems = sh.nitems;
+
+    // ---- scatter: every warp walks all items for its own 32 channels ----
+    if (active && nitems > 0) {
+      float ga[8], gb[8];
+      const float* tg = top_grad + (size_t)c * S;
+      const size_t roi_stride = (size_t)C * S;
+      {
+        const int it = sh.items[0];
+        ldg_row8(tg + (size_t)(it >> 4) * roi_stride + (it & 15) * 8, ga);
+      }
+      if (nitems > 1) {
+        const int it = sh.items[1];
+        ldg_row8(tg + (size_t)(it >> 4) * roi_stride + (it & 15) * 8, gb);
+      }
+      for (int i = 0; i < nitems; i += 2) {
+        {
+          const int it = sh.items[i];
+          const int nn = it >> 4;
+          if (nn != st.n) { bw_load_cols(st, pl.bwdx + nn); st.n = nn; }
+          const float4 rowt = __ldg(pl.tabs + (size_t)nn * 32 + (it & 15));
+          bw_item(plane, W, y_lo, y_hi, ga, rowt, st);
+          if (i + 2 < nitems) {
+            const int it2 = sh.items[i + 2];
+            ldg_row8(tg + (size_t)(it2 >> 4) * roi_stride + (it2 & 15) * 8, ga);
+          }
+        }
+        if (i + 1 < nitems) {
+          const int it = sh.items[i + 1];
+          const int nn = it >> 4;
+          if (nn != st.n) { bw_load_cols(st, pl.bwdx + nn); st.n = nn; }
+          const float4 rowt = __ldg(pl.tabs + (size_t)nn * 32 + (it & 15));
+          bw_item(plane, W, y_lo, y_hi, gb, rowt, st);
+          if (i + 3 < nitems) {
+            const int it2 = sh.items[i + 3];
+            ldg_row8(tg + (size_t)(it2 >> 4) * roi_stride + (it2 & 15) * 8, gb);
           }
         }
       }
-      __syncthreads();  // stage k & 1 and tables k & 1 are free again
     }
-    done += cnt;
-    if (cnt == 0) break;
   }
   __syncthreads();
-  // ---- write the band of the 16 planes: warp w stores channel w ----
-  {
+  // ---- write the band: warp w stores its 32 channels, lanes along the row cells ----
+  if (active) {
     const int n_cells = (y_hi - y_lo) * W;
-    float* g = bottom_grad + ((size_t)img * C + c0 + wid) * H * W + (size_t)y_lo * W;
-    const float* sp = planes + wid * Ppb;
-    for (int i = lane; i < n_cells; i += 32) g[i] = sp[i];
+    for (int ch = 0; ch < 32; ++ch) {
+      float* g = bottom_grad + ((size_t)img * C + cw + ch) * H * W + (size_t)y_lo * W;
+      const float* sp = planes + (size_t)(wid * 32 + ch) * Sb;
+      for (int i = lane; i < n_cells; i += 32) g[i] = sp[i];
+    }
   }
 }
 
@@ -544,13 +693,13 @@ static int check_common(const void* a, const void* b, const void* c, int batch, 
   return TLOD_OK;
 }
 
-static size_t pr_smem_bytes(int hw) {
-  return (size_t)PR_CH * pr_plane_stride(hw) * sizeof(float) + sizeof(PRShared);
+static bool plan_supported(int batch, int height, int width, int ah, int aw) {
+  return batch <= PL_MAXB && ah <= PL_MAXA && aw <= PL_MAXA && height < 32768 &&
+         (long long)height * width < (1LL << 30);
 }
 
-static bool pr_applicable(int batch, int channels, int height, int width, int ah, int aw) {
-  if (channels % PR_CH != 0 || batch > PR_MAXB || ah > PR_MAXA || aw > PR_MAXA) return false;
-  return pr_smem_bytes(height * width) <= (size_t)device_info().max_smem_optin;
+static size_t pr_smem_bytes(int h, int w) {
+  return (size_t)PR_CH * pr_plane_stride(h, w) * sizeof(float) + sizeof(PRShared);
 }
 
 static int generic_launch(bool backward, const float* src, const float* rois, float* dst, int batch,
@@ -579,30 +728,59 @@ static int generic_launch(bool backward, const float* src, const float* rois, fl
 
 using namespace tlod;
 
+extern "C" size_t tlod_roi_align_plan_bytes(int batch, int num_rois) {
+  if (batch <= 0 || num_rois < 0) return 0;
+  return plan_layout(batch, num_rois).total + 256;
+}
+
+extern "C" int tlod_roi_align_plan(const float* rois, int batch, int height, int width, int num_rois,
+                                   int aligned_h, int aligned_w, float spatial_scale, void* plan,
+                                   size_t plan_bytes, void* stream) {
+  if (!plan || (num_rois > 0 && !rois)) return TLOD_ERR_NULL_POINTER;
+  if (batch <= 0 || height < 2 || width < 2 || num_rois < 0 || aligned_h < 2 || aligned_w < 2)
+    return TLOD_ERR_BAD_SHAPE;
+  if (!plan_supported(batch, height, width, aligned_h, aligned_w)) return TLOD_ERR_UNSUPPORTED;
+  if (plan_bytes < tlod_roi_align_plan_bytes(batch, num_rois) || ((uintptr_t)plan & 255))
+    return TLOD_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const PlanPtrs pl = plan_ptrs(plan, batch, num_rois);
+  const int grid = 1 + (num_rois + PL_THREADS / 32 - 1) / (PL_THREADS / 32);
+  {
+    LaunchScope scope("roi_align_plan_kernel", st);
+    roi_align_plan_kernel<<<grid, PL_THREADS, 0, st>>>(rois, pl, batch, height, width, num_rois,
+                                                       aligned_h, aligned_w, spatial_scale);
+  }
+  return last_launch_status();
+}
+
 extern "C" int tlod_roi_align_forward(const float* features, const float* rois, float* output,
                                       int batch, int channels, int height, int width, int num_rois,
                                       int aligned_h, int aligned_w, float spatial_scale,
-                                      void* stream) {
+                                      const void* plan, size_t plan_bytes, void* stream) {
   int rc = check_common(features, rois, output, batch, channels, height, width, num_rois, aligned_h,
                         aligned_w);
   if (rc != TLOD_OK) return rc;
   if (num_rois == 0) return TLOD_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const bool aligned16 = ((uintptr_t)output & 15) == 0;
-  if (pr_applicable(batch, channels, height, width, aligned_h, aligned_w)) {
-    const int Pp = pr_plane_stride(height * width);
-    const size_t smem = pr_smem_bytes(height * width);
+  const bool planned = plan != nullptr && plan_supported(batch, height, width, aligned_h, aligned_w);
+  if (plan && (plan_bytes < tlod_roi_align_plan_bytes(batch, num_rois) || ((uintptr_t)plan & 255)))
+    return TLOD_ERR_WORKSPACE;
+  if (planned && channels % PR_CH == 0 &&
+      pr_smem_bytes(height, width) <= (size_t)device_info().max_smem_optin) {
+    const int Pp = pr_plane_stride(height, width);
+    const size_t smem = pr_smem_bytes(height, width);
     const long long units = (long long)(channels / PR_CH) * num_rois;
     int grid = device_info().sm_count;
     if ((long long)grid > units) grid = (int)units;
-    const bool fast8 = aligned_w == 8 && (aligned_h % 2) == 0 && aligned16;
-    auto kern = fast8 ? roi_align_fwd_planes_kernel<true> : roi_align_fwd_planes_kernel<false>;
+    const bool w8 = aligned_w == 8 && ((uintptr_t)output & 31) == 0;
+    auto kern = w8 ? roi_align_fwd_planes_kernel<true> : roi_align_fwd_planes_kernel<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
+    const PlanPtrs pl = plan_ptrs(const_cast<void*>(plan), batch, num_rois);
     {
       LaunchScope scope("roi_align_fwd_planes_kernel", st);
-      kern<<<grid, PR_THREADS, smem, st>>>(features, rois, output, batch, channels, height, width,
-                                           num_rois, aligned_h, aligned_w, spatial_scale, Pp);
+      kern<<<grid, PR_THREADS, smem, st>>>(features, output, pl, batch, channels, height, width,
+                                           num_rois, aligned_h, aligned_w, Pp);
     }
     return last_launch_status();
   }
@@ -613,45 +791,46 @@ extern "C" int tlod_roi_align_forward(const float* features, const float* rois, 
 extern "C" int tlod_roi_align_backward(const float* top_grad, const float* rois, float* bottom_grad,
                                        int batch, int channels, int height, int width,
                                        int num_rois, int aligned_h, int aligned_w,
-                                       float spatial_scale, void* stream) {
+                                       float spatial_scale, const void* plan, size_t plan_bytes,
+                                       void* stream) {
   int rc = check_common(top_grad, rois, bottom_grad, batch, channels, height, width, num_rois,
                         aligned_h, aligned_w);
   if (rc != TLOD_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t grad_bytes = (size_t)batch * channels * height * width * sizeof(float);
   if (num_rois == 0) return (int)cudaMemsetAsync(bottom_grad, 0, grad_bytes, st);
+  if (plan && (plan_bytes < tlod_roi_align_plan_bytes(batch, num_rois) || ((uintptr_t)plan & 255)))
+    return TLOD_ERR_WORKSPACE;
+  const bool planned = plan != nullptr && plan_supported(batch, height, width, aligned_h, aligned_w);
 
-  // plane-resident path: AW == 8 (one float4 per slot), tiles fetched in 16-byte pieces
-  if (channels % PR_CH == 0 && aligned_w == 8 && aligned_h <= PR_MAXA &&
-      ((uintptr_t)top_grad & 15) == 0) {
-    const int pairs = batch * (channels / PR_CH);
-    const int sms = device_info().sm_count;
-    int nsplit = (2 * sms + pairs - 1) / pairs;  // row bands per plane: fill the machine twice over
-    if (nsplit > 4) nsplit = 4;
-    if (nsplit > height / 8) nsplit = height / 8 > 0 ? height / 8 : 1;
-    if (nsplit < 1) nsplit = 1;
-    const int S = aligned_h * 8;
-    const int TS = (S + 31) / 32 * 32 + 8;  // channel stride of a tile: 8 (mod 32) floats
-    for (; nsplit <= 64; ++nsplit) {  // more bands if the planes do not fit shared memory
-      const int band_rows = (height + nsplit - 1) / nsplit;
-      const int Ppb = pr_plane_stride(band_rows * width);
-      const size_t smem = ((size_t)PR_CH * Ppb + (size_t)2 * PB_NB * PR_CH * TS) * sizeof(float) +
-                          sizeof(PBShared);
-      if (smem > (size_t)device_info().max_smem_optin) {
-        if (band_rows <= 1) break;
-        continue;
+  // band-resident path: AW == 8 (one 32-byte gradient row per item), C % 32 == 0
+  if (planned && channels % 32 == 0 && aligned_w == 8 && ((uintptr_t)top_grad & 15) == 0) {
+    size_t budget = 100 * 1024;  // two CTAs per SM
+    int band_rows = (int)((budget / (BW_CH * sizeof(float)) - 1) / width);
+    if (band_rows < 2) {  // wide maps: one CTA per SM
+      budget = (size_t)device_info().max_smem_optin - sizeof(BWShared) - 1024;
+      band_rows = (int)((budget / (BW_CH * sizeof(float)) - 1) / width);
+    }
+    if (band_rows > height) band_rows = height;
+    if (band_rows >= 1) {
+      const int Sb = (band_rows * width) | 1;  // odd stride: lane = channel is conflict free
+      const int nbands = (height + band_rows - 1) / band_rows;
+      const int ngroups = (channels + BW_CH - 1) / BW_CH;
+      const size_t smem = (size_t)BW_CH * Sb * sizeof(float) + sizeof(BWShared);
+      const long long grid = (long long)batch * ngroups * nbands;
+      if (grid <= 2147483647LL && smem <= (size_t)device_info().max_smem_optin) {
+        cudaError_t e = cudaFuncSetAttribute(roi_align_bwd_planes_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        const PlanPtrs pl = plan_ptrs(const_cast<void*>(plan), batch, num_rois);
+        {
+          LaunchScope scope("roi_align_bwd_planes_kernel", st);
+          roi_align_bwd_planes_kernel<<<(int)grid, BW_THREADS, smem, st>>>(
+              top_grad, bottom_grad, pl, batch, channels, height, width, aligned_h, ngroups, nbands,
+              band_rows, Sb);
+        }
+        return last_launch_status();
       }
-      if ((long long)pairs * nsplit > 2147483647LL) break;
-      cudaError_t e = cudaFuncSetAttribute(roi_align_bwd_planes_kernel,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return (int)e;
-      {
-        LaunchScope scope("roi_align_bwd_planes_kernel", st);
-        roi_align_bwd_planes_kernel<<<pairs * nsplit, PR_THREADS, smem, st>>>(
-            top_grad, rois, bottom_grad, batch, channels, height, width, num_rois, aligned_h,
-            spatial_scale, nsplit, band_rows, Ppb, TS);
-      }
-      return last_launch_status();
     }
   }
   cudaError_t e = cudaMemsetAsync(bottom_grad, 0, grad_bytes, st);

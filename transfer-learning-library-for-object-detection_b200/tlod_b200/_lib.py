@@ -24,8 +24,12 @@ SIGNATURES = {
     "tlod_profile_collect": (c_int, []),
     "tlod_profile_get": (c_int, [c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_double),
                                  ctypes.POINTER(c_longlong)]),
-    "tlod_roi_align_forward": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P]),
-    "tlod_roi_align_backward": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P]),
+    "tlod_roi_align_plan_bytes": (c_size_t, [c_int, c_int]),
+    "tlod_roi_align_plan": (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P, c_size_t, P]),
+    "tlod_roi_align_forward": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P,
+                                       c_size_t, P]),
+    "tlod_roi_align_backward": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P,
+                                        c_size_t, P]),
     "tlod_roi_pool_forward": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P]),
     "tlod_roi_pool_backward": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P]),
     "tlod_nms_workspace_bytes": (c_size_t, [c_int]),

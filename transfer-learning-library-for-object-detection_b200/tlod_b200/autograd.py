@@ -14,16 +14,22 @@ class RoIAlignFunction(Function):
 
     @staticmethod
     def forward(ctx, features, rois, aligned_height, aligned_width, spatial_scale):
-        ctx.save_for_backward(rois)
         ctx.feature_size = tuple(features.shape)
         ctx.scale = float(spatial_scale)
-        return F.roi_align_forward(features, rois, int(aligned_height), int(aligned_width), ctx.scale)
+        # the plan (sampling tables, image-sorted RoI list) is built once and reused by backward
+        plan = F.roi_align_plan(rois, ctx.feature_size, int(aligned_height), int(aligned_width), ctx.scale)
+        ctx.has_plan = plan is not None
+        ctx.save_for_backward(rois, *([plan] if ctx.has_plan else []))
+        return F.roi_align_forward(features, rois, int(aligned_height), int(aligned_width), ctx.scale,
+                                   plan=plan, use_plan=ctx.has_plan)
 
     @staticmethod
     def backward(ctx, grad_output):
-        (rois,) = ctx.saved_tensors
+        rois = ctx.saved_tensors[0]
+        plan = ctx.saved_tensors[1] if ctx.has_plan else None
         assert grad_output.is_cuda  # functions/roi_align.py:38
-        grad_input = F.roi_align_backward(grad_output, rois, ctx.feature_size, ctx.scale)
+        grad_input = F.roi_align_backward(grad_output, rois, ctx.feature_size, ctx.scale, plan=plan,
+                                          use_plan=ctx.has_plan)
         return grad_input, None, None, None, None
 
 

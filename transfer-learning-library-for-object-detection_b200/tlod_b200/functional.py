@@ -51,30 +51,56 @@ def _workspace(device, nbytes: int, tag: str) -> torch.Tensor:
 # ---------------------------------------------------------------------------
 # RoIAlign / RoIPool
 # ---------------------------------------------------------------------------
-def roi_align_forward(features, rois, aligned_h: int, aligned_w: int, spatial_scale: float):
-    _require_cuda(features, rois)
+def roi_align_plan(rois, feature_size, aligned_h: int, aligned_w: int, spatial_scale: float):
+    """Per-`rois` plan (sampling tables, image-sorted RoI list, backward column chains) shared by
+    roi_align_forward and roi_align_backward.  Returns None where the planned kernels do not
+    apply (the generic kernels are used then)."""
+    _require_cuda(rois)
+    rois = _f32(rois)
+    B, _, H, W = [int(v) for v in feature_size]
+    R = rois.size(0)
+    if R == 0 or B > 1024 or aligned_h > 16 or aligned_w > 16:
+        return None
+    nbytes = lib.tlod_roi_align_plan_bytes(B, R)
+    plan = torch.empty((nbytes,), dtype=torch.uint8, device=rois.device)
+    with torch.cuda.device(rois.device):
+        check(lib.tlod_roi_align_plan(rois.data_ptr(), B, H, W, R, int(aligned_h), int(aligned_w),
+                                      float(spatial_scale), plan.data_ptr(), plan.numel(), _stream(rois.device)),
+              "tlod_roi_align_plan")
+    return plan
+
+
+def roi_align_forward(features, rois, aligned_h: int, aligned_w: int, spatial_scale: float, plan=None,
+                      use_plan: bool = True):
+    _require_cuda(features, rois, plan)
     features, rois = _f32(features), _f32(rois)
     if rois.dim() != 2 or rois.size(1) != 5:
         raise ValueError("rois must be (R, 5) [batch_idx, x1, y1, x2, y2]")
     B, C, H, W = features.shape
     R = rois.size(0)
     out = torch.empty((R, C, aligned_h, aligned_w), dtype=torch.float32, device=features.device)
+    if plan is None and use_plan:
+        plan = roi_align_plan(rois, features.shape, aligned_h, aligned_w, spatial_scale)
     with torch.cuda.device(features.device):
         check(lib.tlod_roi_align_forward(features.data_ptr(), rois.data_ptr(), out.data_ptr(), B, C, H, W, R,
                                          int(aligned_h), int(aligned_w), float(spatial_scale),
+                                         _ptr(plan), 0 if plan is None else plan.numel(),
                                          _stream(features.device)), "tlod_roi_align_forward")
     return out
 
 
-def roi_align_backward(top_grad, rois, feature_size, spatial_scale: float):
-    _require_cuda(top_grad, rois)
+def roi_align_backward(top_grad, rois, feature_size, spatial_scale: float, plan=None, use_plan: bool = True):
+    _require_cuda(top_grad, rois, plan)
     top_grad, rois = _f32(top_grad), _f32(rois)
     B, C, H, W = [int(v) for v in feature_size]
     R, _, AH, AW = top_grad.shape
     grad = torch.empty((B, C, H, W), dtype=torch.float32, device=top_grad.device)
+    if plan is None and use_plan:
+        plan = roi_align_plan(rois, feature_size, AH, AW, spatial_scale)
     with torch.cuda.device(top_grad.device):
         check(lib.tlod_roi_align_backward(top_grad.data_ptr(), rois.data_ptr(), grad.data_ptr(), B, C, H, W, R,
-                                          AH, AW, float(spatial_scale), _stream(top_grad.device)),
+                                          AH, AW, float(spatial_scale), _ptr(plan),
+                                          0 if plan is None else plan.numel(), _stream(top_grad.device)),
               "tlod_roi_align_backward")
     return grad
 
