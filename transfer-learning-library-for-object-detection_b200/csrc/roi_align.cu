@@ -32,6 +32,10 @@
 //    planes too large for shared memory, aligned size > 16, no plan): one CTA per
 //    (RoI, channel block), geometry hoisted to shared memory, coalesced output, fp32
 //    atomics in the backward.
+#include <cuda.h>
+
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace tlod {
@@ -162,7 +166,7 @@ __global__ void __launch_bounds__(PL_THREADS)
   if (blockIdx.x == 0) {
     __shared__ int cnt[PL_MAXB + 2];
     __shared__ int next[PL_MAXB + 2];
-    __shared__ int carry;
+  
     for (int i = tid; i <= B; i += PL_THREADS) cnt[i] = 0;
     __syncthreads();
     for (int i = tid; i < R; i += PL_THREADS) atomicAdd(&cnt[roi_image(rois, i, B)], 1);
@@ -185,7 +189,7 @@ __global__ void __launch_bounds__(PL_THREADS)
       }
       if (lane == 0) {
         pl.cum[B + 1] = run;
-        carry = run;
+
       }
     }
     __syncthreads();
@@ -305,40 +309,63 @@ __device__ __forceinline__ void st_global_v8(float* p, const float (&o)[8]) {
                : "memory");
 }
 
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+template <int IMM>
+__device__ __forceinline__ float lds_f32_imm(unsigned addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(IMM));
+  return v;
+}
+
 // One warp, one RoI, 16 channels, AW == 8: lane (c, slot) produces the whole 8-wide output
 // rows ph = 2j + slot of channel c and writes each with one 256-bit store (a lane pair
 // covers 64 contiguous bytes).  Slot 0 reads its cell pairs as (x, x+1), slot 1 as (x+1, x):
 // with the even row stride that alone makes every gather bank-conflict free.
-__device__ __forceinline__ void pr_fwd_roi_w8(const float* __restrict__ plane, int Wp,
+// Addresses are 32-bit shared-window byte addresses; WP > 0 is the compile-time row stride
+// (the second row of a sample is then an immediate offset), WP == 0 the run-time one.
+template <int WP>
+__device__ __forceinline__ void pr_fwd_roi_w8(unsigned plane_addr, int Wp_rt,
                                               const float4* __restrict__ wtab, int AH, int slot,
-                                              float* __restrict__ out_c /* channel c of the RoI */) {
-  int xa[8], xb[8];
+                                              float* __restrict__ out_c /* channel c of the RoI */,
+                                              int dbg) {
+  unsigned ca[8], cb[8];
   float wp[8], wq[8];
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const float4 m = wtab[16 + q];
     int x = __float_as_int(m.x);
     x = x < 0 ? 0 : x;
-    xa[q] = x + slot;
-    xb[q] = x + (slot ^ 1);
+    ca[q] = plane_addr + 4u * (unsigned)(x + slot);
+    cb[q] = plane_addr + 4u * (unsigned)(x + (slot ^ 1));
     wp[q] = slot ? m.z : m.y;
     wq[q] = slot ? m.y : m.z;
   }
+  const unsigned row_bytes = 4u * (unsigned)(WP > 0 ? WP : Wp_rt);
   for (int j = 0; 2 * j < AH; ++j) {
     const int ph = min(2 * j + slot, AH - 1);
     const float4 r = wtab[ph];
-    const float* b0 = plane + __float_as_int(r.x);
-    const float* b1 = b0 + Wp;
+    const unsigned ro = (unsigned)__float_as_int(r.x);  // byte offset of the first sampled row
     float o[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const float p00 = b0[xa[q]], p01 = b0[xb[q]];
-      const float p10 = b1[xa[q]], p11 = b1[xb[q]];
+      const unsigned a = ca[q] + ro, b = cb[q] + ro;
+      float p00, p01, p10, p11;
+      if (WP > 0) {
+        p00 = lds_f32(a); p01 = lds_f32(b);
+        p10 = lds_f32_imm<4 * WP>(a); p11 = lds_f32_imm<4 * WP>(b);
+      } else {
+        p00 = lds_f32(a); p01 = lds_f32(b);
+        p10 = lds_f32(a + row_bytes); p11 = lds_f32(b + row_bytes);
+      }
       const float t0 = fmaf(p01, wq[q], p00 * wp[q]);
       const float t1 = fmaf(p11, wq[q], p10 * wp[q]);
       o[q] = fmaf(t1, r.z, t0 * r.y);
     }
-    if (2 * j + slot < AH) st_global_v8(out_c + ph * 8, o);
+    if (2 * j + slot < AH && dbg != 1) st_global_v8(out_c + ph * 8, o);
   }
 }
 
@@ -368,11 +395,13 @@ __device__ __forceinline__ void pr_fwd_roi_any(const float* __restrict__ plane, 
   }
 }
 
-template <bool W8>
+// W8: 0 = any aligned width (<= 16); 1 = aligned_w == 8; 76 = aligned_w == 8 and a padded row
+// stride of 76 floats (W = 75 or 76: the 600x1200 / stride-16 maps) as a compile-time constant.
+template <int W8>
 __global__ void __launch_bounds__(PR_THREADS, 1)
     roi_align_fwd_planes_kernel(const float* __restrict__ features, float* __restrict__ output,
                                 PlanPtrs pl, int B, int C, int H, int W, int R, int AH, int AW,
-                                int Pp) {
+                                int Pp, int dbg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* planes = reinterpret_cast<float*>(smem_raw);
   PRShared& sh = *reinterpret_cast<PRShared*>(smem_raw + (size_t)PR_CH * Pp * sizeof(float));
@@ -438,6 +467,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1)
 
     const int base = __ldg(cum + img);
     const float* plane = planes + c * Pp;
+    const unsigned plane_addr = (unsigned)__cvta_generic_to_shared(plane);
     float4* wtab = sh.wtab[wid];
     int e = r_lo + wid;
     int n = (e < r_hi) ? __ldg(pl.list + base + e) : 0;
@@ -453,18 +483,18 @@ __global__ void __launch_bounds__(PR_THREADS, 1)
       if (img == B) {  // invalid image index: zeros
         for (int i = lane; i < PR_CH * S; i += 32) out_roi[i] = 0.f;
       } else {
-        // rows: cell offset of the first sampled row in the padded plane (0 if out of range:
-        // the weights are zero then)
+        // rows: offset of the first sampled row in the padded plane (0 if out of range: the
+        // weights are zero then); bytes for the aligned_w == 8 path, cells otherwise
         if (lane < 16) {
           const int start = __float_as_int(t.w);
-          t.x = __int_as_float(start < 0 ? 0 : start * Wp);
+          t.x = __int_as_float(start < 0 ? 0 : start * Wp * (W8 ? 4 : 1));
         }
         wtab[lane] = t;
         __syncwarp();
-        if (W8)
-          pr_fwd_roi_w8(plane, Wp, wtab, AH, slot, out_roi + (size_t)c * S);
-        else
+        if (W8 == 0)
           pr_fwd_roi_any(plane, Wp, wtab, AH, AW, slot, out_roi + (size_t)c * S);
+        else
+          pr_fwd_roi_w8<(W8 > 1 ? W8 : 0)>(plane_addr, Wp, wtab, AH, slot, out_roi + (size_t)c * S, dbg);
         __syncwarp();
       }
       n = n2;
@@ -478,22 +508,62 @@ __global__ void __launch_bounds__(PR_THREADS, 1)
 // ===========================================================================
 // band-resident backward (no atomics)
 // ===========================================================================
-constexpr int BW_WARPS = 4;
-constexpr int BW_THREADS = BW_WARPS * 32;
-constexpr int BW_CH = BW_WARPS * 32;  // channels per CTA
-constexpr int BW_CHUNK = BW_THREADS;  // RoIs examined per round
+// Work unit ("item") = one 8-wide gradient row (RoI n, output row ph): it scatters into plane
+// rows y0 and y0 + 1.  A CTA walks the items whose rows intersect its band.  The 32-byte
+// gradient rows of the CTA's 128 channels (4 KB, 256 B apart in HBM) are fetched by TMA
+// (4-D tensor map over (R, C, AH, 8), box 8 x 1 x 128 x 1, 32-byte swizzle) into a ring of
+// shared-memory stages by a producer warp; the four consumer warps read their lane's row with
+// two conflict-free LDS.128 and release the stage.
+constexpr int BW_WARPS = 4;                    // consumer warps
+constexpr int BW_THREADS = BW_WARPS * 32 + 32;  // + 1 producer warp
+constexpr int BW_CH = BW_WARPS * 32;            // channels per CTA
+constexpr int BW_CHUNK = BW_WARPS * 32;         // RoIs examined per round
+constexpr int BW_STAGES = 6;
+constexpr int BW_STAGE_BYTES = BW_CH * 32;
 
 struct BWShared {
   int items[BW_CHUNK * 16];  // (roi << 4) | ph, in (list order, ph) order
   int warp_sums[BW_WARPS];
   int nitems;
+  unsigned long long full_bar[BW_STAGES];
+  unsigned long long empty_bar[BW_STAGES];
 };
 
-__device__ __forceinline__ void ldg_row8(const float* __restrict__ p, float (&g)[8]) {
-  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
-  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-  g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w;
-  g[4] = b.x; g[5] = b.y; g[6] = b.z; g[7] = b.w;
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned addr = smem_u32(bar);
+  unsigned done = 0;
+  // bounded: a lost TMA transaction must fault the launch, not hang the device
+  for (unsigned spins = 0; !done; ++spins) {
+    if (spins > (1u << 24)) __trap();
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, unsigned long long* bar,
+                                            int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"((unsigned long long)tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
 }
 
 struct BwdState {
@@ -527,31 +597,36 @@ __device__ __forceinline__ void bw_load_cols(BwdState& s, const BwdCols* __restr
 }
 
 // Add rw * (emitted cell values) into one plane row.  All enabled cells are distinct, so
-// the loads are issued together, then the stores.
+// the loads are issued together, then the stores.  ALLJ: every one of the 16 cells is enabled.
+template <bool ALLJ>
 __device__ __forceinline__ void bw_rmw_row(float* __restrict__ row, float rw, const BwdState& s,
                                            const float (&e0)[9], const float (&e1)[9]) {
   float o0[9], o1[9];
 #pragma unroll
   for (int t = 1; t <= 8; ++t) {
-    o0[t] = ((s.en0 >> t) & 1u) ? row[s.ex[t]] : 0.f;
-    o1[t] = ((s.en1 >> t) & 1u) ? row[s.ex[t] + 1] : 0.f;
+    o0[t] = (ALLJ || ((s.en0 >> t) & 1u)) ? row[s.ex[t]] : 0.f;
+    o1[t] = (ALLJ || ((s.en1 >> t) & 1u)) ? row[s.ex[t] + 1] : 0.f;
   }
 #pragma unroll
   for (int t = 1; t <= 8; ++t) {
-    if ((s.en0 >> t) & 1u) row[s.ex[t]] = fmaf(rw, e0[t], o0[t]);
-    if ((s.en1 >> t) & 1u) row[s.ex[t] + 1] = fmaf(rw, e1[t], o1[t]);
+    if (ALLJ || ((s.en0 >> t) & 1u)) row[s.ex[t]] = fmaf(rw, e0[t], o0[t]);
+    if (ALLJ || ((s.en1 >> t) & 1u)) row[s.ex[t] + 1] = fmaf(rw, e1[t], o1[t]);
   }
 }
 
 __device__ __forceinline__ void bw_item(float* __restrict__ plane, int W, int y_lo, int y_hi,
                                         const float (&g)[8], const float4 rowt, const BwdState& s) {
   float e0[9], e1[9];
+  const int y0 = __float_as_int(rowt.w);
+  const bool in0 = y0 >= y_lo && y0 < y_hi, in1 = y0 + 1 >= y_lo && y0 + 1 < y_hi;
   if (s.all_jump) {
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
       e0[t + 1] = g[t] * s.cw0[t];
       e1[t + 1] = g[t] * s.cw1[t];
     }
+    if (in0) bw_rmw_row<true>(plane + (y0 - y_lo) * W, rowt.y, s, e0, e1);
+    if (in1) bw_rmw_row<true>(plane + (y0 + 1 - y_lo) * W, rowt.z, s, e0, e1);
   } else {
     float a0 = 0.f, a1 = 0.f;
 #pragma unroll
@@ -562,42 +637,53 @@ __device__ __forceinline__ void bw_item(float* __restrict__ plane, int W, int y_
       a0 = na0;
     }
     e0[8] = a0; e1[8] = a1;
+    if (in0) bw_rmw_row<false>(plane + (y0 - y_lo) * W, rowt.y, s, e0, e1);
+    if (in1) bw_rmw_row<false>(plane + (y0 + 1 - y_lo) * W, rowt.z, s, e0, e1);
   }
-  const int y0 = __float_as_int(rowt.w);
-  if (y0 >= y_lo && y0 < y_hi) bw_rmw_row(plane + (y0 - y_lo) * W, rowt.y, s, e0, e1);
-  if (y0 + 1 >= y_lo && y0 + 1 < y_hi) bw_rmw_row(plane + (y0 + 1 - y_lo) * W, rowt.z, s, e0, e1);
 }
 
 __global__ void __launch_bounds__(BW_THREADS)
-    roi_align_bwd_planes_kernel(const float* __restrict__ top_grad, float* __restrict__ bottom_grad,
+    roi_align_bwd_planes_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ bottom_grad,
                                 PlanPtrs pl, int B, int C, int H, int W, int AH, int ngroups,
                                 int nbands, int band_rows, int Sb) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* planes = reinterpret_cast<float*>(smem_raw);
-  BWShared& sh = *reinterpret_cast<BWShared*>(smem_raw + (size_t)BW_CH * Sb * sizeof(float));
+  extern __shared__ __align__(1024) unsigned char smem_bw[];
+  // [stages][planes][BWShared]: the TMA stages need 256-byte alignment for the 32-byte swizzle
+  unsigned char* stages = smem_bw;
+  float* planes = reinterpret_cast<float*>(smem_bw + BW_STAGES * BW_STAGE_BYTES);
+  BWShared& sh = *reinterpret_cast<BWShared*>(smem_bw + BW_STAGES * BW_STAGE_BYTES +
+                                              ((size_t)BW_CH * Sb * sizeof(float) + 15) / 16 * 16);
   const int tid = threadIdx.x, lane = lane_id(), wid = warp_id();
   const int band = blockIdx.x % nbands;
   const int rest = blockIdx.x / nbands;
   const int grp = rest % ngroups, img = rest / ngroups;
   const int y_lo = band * band_rows, y_hi = min(H, y_lo + band_rows);
-  const int cw = grp * BW_CH + wid * 32;  // first channel of this warp
-  const bool active = cw < C;             // C % 32 == 0
-  const int c = cw + lane;
-  float* plane = planes + (size_t)(wid * 32 + lane) * Sb;
+  const bool producer = wid == BW_WARPS;
+  const int cw = grp * BW_CH + wid * 32;       // first channel of this consumer warp
+  const bool active = !producer && cw < C;     // C % 32 == 0
+  const int n_active = min(BW_WARPS, (C - grp * BW_CH) / 32);
+  float* plane = planes + (size_t)((wid & (BW_WARPS - 1)) * 32 + lane) * Sb;
 
+  if (tid == 0) {
+    for (int s = 0; s < BW_STAGES; ++s) {
+      mbar_init(&sh.full_bar[s], 1);
+      mbar_init(&sh.empty_bar[s], n_active);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   for (int i = tid; i < BW_CH * Sb; i += BW_THREADS) planes[i] = 0.f;
+  __syncthreads();
 
   const int base = __ldg(pl.cum + img);
   const int n_img = __ldg(pl.cum + img + 1) - base;
-  const int S = AH * 8;
   BwdState st;
   st.n = -1;
+  unsigned it0 = 0;  // items issued / consumed before this chunk (stage = it % BW_STAGES)
 
   for (int chunk = 0; chunk < n_img; chunk += BW_CHUNK) {
     // ---- items of this chunk: (RoI, ph) whose rows y0 / y0+1 intersect the band ----
     unsigned mask = 0u;
     int n = 0;
-    if (chunk + tid < n_img) {
+    if (!producer && chunk + tid < n_img) {
       n = __ldg(pl.list + base + chunk + tid);
       const int4* yr = reinterpret_cast<const int4*>(pl.yrow + (size_t)n * 16);
       const int4 a = __ldg(yr), b = __ldg(yr + 1);
@@ -615,59 +701,59 @@ __global__ void __launch_bounds__(BW_THREADS)
       const int t = __shfl_up_sync(0xffffffffu, incl, d);
       if (lane >= d) incl += t;
     }
-    if (lane == 31) sh.warp_sums[wid] = incl;
+    if (!producer && lane == 31) sh.warp_sums[wid] = incl;
     __syncthreads();  // also orders the previous round's item reads before this round's writes
-    int pos = incl - cnt;
+    if (!producer) {
+      int pos = incl - cnt;
 #pragma unroll
-    for (int w = 0; w < BW_WARPS; ++w)
-      if (w < wid) pos += sh.warp_sums[w];
-    if (tid == BW_THREADS - 1) sh.nitems = pos + cnt;
-    while (mask) {
-      const int k = __ffs(mask) - 1;
-      mask &= mask - 1u;
-      sh.items[pos++] = (n << 4) | k;
+      for (int w = 0; w < BW_WARPS; ++w)
+        if (w < wid) pos += sh.warp_sums[w];
+      if (tid == BW_WARPS * 32 - 1) sh.nitems = pos + cnt;
+      while (mask) {
+        const int k = __ffs(mask) - 1;
+        mask &= mask - 1u;
+        sh.items[pos++] = (n << 4) | k;
+      }
     }
     __syncthreads();
     const int nitems = sh.nitems;
 
-    // ---- scatter: every warp walks all items for its own 32 channels ----
-    if (active && nitems > 0) {
-      float ga[8], gb[8];
-      const float* tg = top_grad + (size_t)c * S;
-      const size_t roi_stride = (size_t)C * S;
-      {
-        const int it = sh.items[0];
-        ldg_row8(tg + (size_t)(it >> 4) * roi_stride + (it & 15) * 8, ga);
-      }
-      if (nitems > 1) {
-        const int it = sh.items[1];
-        ldg_row8(tg + (size_t)(it >> 4) * roi_stride + (it & 15) * 8, gb);
-      }
-      for (int i = 0; i < nitems; i += 2) {
-        {
-          const int it = sh.items[i];
-          const int nn = it >> 4;
-          if (nn != st.n) { bw_load_cols(st, pl.bwdx + nn); st.n = nn; }
-          const float4 rowt = __ldg(pl.tabs + (size_t)nn * 32 + (it & 15));
-          bw_item(plane, W, y_lo, y_hi, ga, rowt, st);
-          if (i + 2 < nitems) {
-            const int it2 = sh.items[i + 2];
-            ldg_row8(tg + (size_t)(it2 >> 4) * roi_stride + (it2 & 15) * 8, ga);
-          }
+    if (producer) {
+      if (lane == 0) {
+        for (int i = 0; i < nitems; ++i) {
+          const unsigned it = it0 + (unsigned)i;
+          const int s = it % BW_STAGES;
+          const unsigned ph = (it / BW_STAGES) & 1u;
+          mbar_wait(&sh.empty_bar[s], ph ^ 1u);
+          mbar_arrive_expect_tx(&sh.full_bar[s], BW_STAGE_BYTES);
+          const int item = sh.items[i];
+          tma_load_4d(stages + s * BW_STAGE_BYTES, &tmap, &sh.full_bar[s], 0, item & 15, grp * BW_CH,
+                      item >> 4);
         }
-        if (i + 1 < nitems) {
-          const int it = sh.items[i + 1];
-          const int nn = it >> 4;
-          if (nn != st.n) { bw_load_cols(st, pl.bwdx + nn); st.n = nn; }
-          const float4 rowt = __ldg(pl.tabs + (size_t)nn * 32 + (it & 15));
-          bw_item(plane, W, y_lo, y_hi, gb, rowt, st);
-          if (i + 3 < nitems) {
-            const int it2 = sh.items[i + 3];
-            ldg_row8(tg + (size_t)(it2 >> 4) * roi_stride + (it2 & 15) * 8, gb);
-          }
-        }
+      }
+    } else if (active) {
+      // ---- scatter: every consumer warp walks all items for its own 32 channels ----
+      // lane's 32-byte row inside a stage, 16-byte halves swapped by the 32-byte swizzle
+      const int r = wid * 32 + lane;
+      const int sw = ((r >> 2) & 1) << 4;
+      for (int i = 0; i < nitems; ++i) {
+        const unsigned it = it0 + (unsigned)i;
+        const int s = it % BW_STAGES;
+        const int item = sh.items[i];
+        const int nn = item >> 4;
+        if (nn != st.n) { bw_load_cols(st, pl.bwdx + nn); st.n = nn; }
+        const float4 rowt = __ldg(pl.tabs + (size_t)nn * 32 + (item & 15));
+        mbar_wait(&sh.full_bar[s], (it / BW_STAGES) & 1u);
+        const unsigned char* tile = stages + s * BW_STAGE_BYTES + r * 32;
+        const float4 ga = *reinterpret_cast<const float4*>(tile + sw);
+        const float4 gb = *reinterpret_cast<const float4*>(tile + (sw ^ 16));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh.empty_bar[s]);
+        const float g[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+        bw_item(plane, W, y_lo, y_hi, g, rowt, st);
       }
     }
+    it0 += (unsigned)nitems;
   }
   __syncthreads();
   // ---- write the band: warp w stores its 32 channels, lanes along the row cells ----
@@ -700,6 +786,36 @@ static bool plan_supported(int batch, int height, int width, int ah, int aw) {
 
 static size_t pr_smem_bytes(int h, int w) {
   return (size_t)PR_CH * pr_plane_stride(h, w) * sizeof(float) + sizeof(PRShared);
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &p, 12000, cudaEnableDefault, &q) !=
+            cudaSuccess || q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+// (R, C, AH, 8) fp32 gradient tensor; box = one 8-wide row of BW_CH consecutive channels
+static bool make_grad_tmap(CUtensorMap* map, const float* top_grad, int R, int C, int AH) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[4] = {8, (cuuint64_t)AH, (cuuint64_t)C, (cuuint64_t)R};
+  const cuuint64_t strides[3] = {32, (cuuint64_t)AH * 32, (cuuint64_t)C * AH * 32};
+  const cuuint32_t box[4] = {8, 1, (cuuint32_t)BW_CH, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(top_grad), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 static int generic_launch(bool backward, const float* src, const float* rois, float* dst, int batch,
@@ -773,14 +889,17 @@ extern "C" int tlod_roi_align_forward(const float* features, const float* rois, 
     int grid = device_info().sm_count;
     if ((long long)grid > units) grid = (int)units;
     const bool w8 = aligned_w == 8 && ((uintptr_t)output & 31) == 0;
-    auto kern = w8 ? roi_align_fwd_planes_kernel<true> : roi_align_fwd_planes_kernel<false>;
+    auto kern = !w8 ? roi_align_fwd_planes_kernel<0>
+                    : (pr_row_stride(width) == 76 ? roi_align_fwd_planes_kernel<76>
+                                                  : roi_align_fwd_planes_kernel<1>);
+    static const int dbg = getenv("TLOD_FWD_DEBUG") ? atoi(getenv("TLOD_FWD_DEBUG")) : 0;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     const PlanPtrs pl = plan_ptrs(const_cast<void*>(plan), batch, num_rois);
     {
       LaunchScope scope("roi_align_fwd_planes_kernel", st);
       kern<<<grid, PR_THREADS, smem, st>>>(features, output, pl, batch, channels, height, width,
-                                           num_rois, aligned_h, aligned_w, Pp);
+                                           num_rois, aligned_h, aligned_w, Pp, dbg);
     }
     return last_launch_status();
   }
@@ -805,18 +924,21 @@ extern "C" int tlod_roi_align_backward(const float* top_grad, const float* rois,
 
   // band-resident path: AW == 8 (one 32-byte gradient row per item), C % 32 == 0
   if (planned && channels % 32 == 0 && aligned_w == 8 && ((uintptr_t)top_grad & 15) == 0) {
-    size_t budget = 100 * 1024;  // two CTAs per SM
+    const size_t fixed = sizeof(BWShared) + BW_STAGES * BW_STAGE_BYTES + 64;
+    size_t budget = 112 * 1024 - fixed;  // two CTAs per SM
     int band_rows = (int)((budget / (BW_CH * sizeof(float)) - 1) / width);
     if (band_rows < 2) {  // wide maps: one CTA per SM
-      budget = (size_t)device_info().max_smem_optin - sizeof(BWShared) - 1024;
+      budget = (size_t)device_info().max_smem_optin - fixed - 1024;
       band_rows = (int)((budget / (BW_CH * sizeof(float)) - 1) / width);
     }
     if (band_rows > height) band_rows = height;
-    if (band_rows >= 1) {
+    CUtensorMap tmap;
+    if (band_rows >= 1 && make_grad_tmap(&tmap, top_grad, num_rois, channels, aligned_h)) {
       const int Sb = (band_rows * width) | 1;  // odd stride: lane = channel is conflict free
       const int nbands = (height + band_rows - 1) / band_rows;
       const int ngroups = (channels + BW_CH - 1) / BW_CH;
-      const size_t smem = (size_t)BW_CH * Sb * sizeof(float) + sizeof(BWShared);
+      const size_t smem = BW_STAGES * BW_STAGE_BYTES + ((size_t)BW_CH * Sb * sizeof(float) + 15) / 16 * 16 +
+                          sizeof(BWShared);
       const long long grid = (long long)batch * ngroups * nbands;
       if (grid <= 2147483647LL && smem <= (size_t)device_info().max_smem_optin) {
         cudaError_t e = cudaFuncSetAttribute(roi_align_bwd_planes_kernel,
@@ -826,7 +948,7 @@ extern "C" int tlod_roi_align_backward(const float* top_grad, const float* rois,
         {
           LaunchScope scope("roi_align_bwd_planes_kernel", st);
           roi_align_bwd_planes_kernel<<<(int)grid, BW_THREADS, smem, st>>>(
-              top_grad, bottom_grad, pl, batch, channels, height, width, aligned_h, ngroups, nbands,
+              tmap, bottom_grad, pl, batch, channels, height, width, aligned_h, ngroups, nbands,
               band_rows, Sb);
         }
         return last_launch_status();
