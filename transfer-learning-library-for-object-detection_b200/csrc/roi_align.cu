@@ -107,15 +107,16 @@ constexpr int PL_THREADS = 256;
 //     a0' = g*cw0[t] + ms[t]*a0 + mh[t]*a1        a1' = g*cw1[t] + ms[t]*a1
 // (same cell: ms=1; moved right by one: mh=1; jumped: both 0).  Before sample t (t = 1..7)
 // and after the last one (t = 8) the accumulators that fall out of the window are final:
-// a0 -> cell ex[t] if bit t of en0, a1 -> cell ex[t] + 1 if bit t of en1.  All cells emitted
-// for one row are distinct, so their read-modify-writes are independent.
+// a0 -> cell ex[t], a1 -> cell ex[t] + 1 ("sites" 2(t-1) and 2(t-1)+1; a site that is not
+// emitted has offset -1).  All cells emitted for one row are distinct, so their
+// read-modify-writes are independent.
 struct __align__(16) BwdCols {
   float cw0[8], cw1[8], ms[8], mh[8];
-  int ex[9];
-  unsigned en0, en1;
-  int all_jump;  // every valid sample starts a new pair of cells: chain is the identity
+  int soff[16];  // site 2(t-1)+k (t = 1..8, k = 0/1): byte offset (ex[t] + k) * 4 in the row, -1 = off
+  int all_jump;  // every sample is valid and starts a new pair of cells: the chain is the identity
+  int pad[3];
 };
-static_assert(sizeof(BwdCols) == 176, "BwdCols layout");
+static_assert(sizeof(BwdCols) == 208, "BwdCols layout");
 
 struct PlanLayout {
   size_t cum, list, yrow, tabs, bwdx, total;
@@ -272,11 +273,16 @@ __global__ void __launch_bounds__(PL_THREADS)
     }
     if (cur >= 0) { en0 |= 1u << 8; en1 |= 1u << 8; ex8 = cur; }
     BwdCols* bc = pl.bwdx + n;
+    // lane t (0..7) holds ex of transition t; sites belong to transitions 1..8
+    const int ex_next = __shfl_down_sync(0xffffffffu, my_ex, 1);  // lane t: ex[t + 1]
     if (lane < 8) {
       bc->cw0[lane] = my_cw0; bc->cw1[lane] = my_cw1; bc->ms[lane] = my_ms; bc->mh[lane] = my_mh;
-      bc->ex[lane] = my_ex;
+      const int t = lane + 1;
+      const int ex = (t == 8) ? ex8 : ex_next;
+      bc->soff[2 * lane] = ((en0 >> t) & 1u) ? ex * 4 : -1;
+      bc->soff[2 * lane + 1] = ((en1 >> t) & 1u) ? (ex + 1) * 4 : -1;
     } else if (lane == 8) {
-      bc->ex[8] = ex8; bc->en0 = en0; bc->en1 = en1; bc->all_jump = all_jump;
+      bc->all_jump = all_jump;
     }
   }
 }
@@ -519,7 +525,9 @@ constexpr int BW_THREADS = BW_WARPS * 32 + 32;  // + 1 producer warp
 constexpr int BW_CH = BW_WARPS * 32;            // channels per CTA
 constexpr int BW_CHUNK = BW_WARPS * 32;         // RoIs examined per round
 constexpr int BW_STAGES = 6;
-constexpr int BW_STAGE_BYTES = BW_CH * 32;
+constexpr int BW_TILE_BYTES = BW_CH * 32;
+constexpr int BW_META_BYTES = 256;  // BwdCols (208) + row table entry (16), padded
+constexpr int BW_STAGE_BYTES = BW_TILE_BYTES + BW_META_BYTES;
 
 struct BWShared {
   int items[BW_CHUNK * 16];  // (roi << 4) | ph, in (list order, ph) order
@@ -557,6 +565,13 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         : "memory");
   }
 }
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes,
+                                          unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, unsigned long long* bar,
                                             int c0, int c1, int c2, int c3) {
   asm volatile(
@@ -568,17 +583,16 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, un
 
 struct BwdState {
   float cw0[8], cw1[8], ms[8], mh[8];
-  int ex[9];
-  unsigned en0, en1;
+  int soff[16];
   int all_jump;
   int n;
 };
 
-__device__ __forceinline__ void bw_load_cols(BwdState& s, const BwdCols* __restrict__ bc) {
-  const float4* q = reinterpret_cast<const float4*>(bc);
-  float4 v[11];
+// per-RoI column state from the stage's metadata block (all lanes read the same 208 bytes)
+__device__ __forceinline__ void bw_load_cols(BwdState& s, const float4* __restrict__ q) {
+  float4 v[13];
 #pragma unroll
-  for (int i = 0; i < 11; ++i) v[i] = __ldg(q + i);
+  for (int i = 0; i < 13; ++i) v[i] = q[i];
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     s.cw0[4 * i] = v[i].x; s.cw0[4 * i + 1] = v[i].y; s.cw0[4 * i + 2] = v[i].z; s.cw0[4 * i + 3] = v[i].w;
@@ -586,59 +600,87 @@ __device__ __forceinline__ void bw_load_cols(BwdState& s, const BwdCols* __restr
     s.ms[4 * i] = v[4 + i].x; s.ms[4 * i + 1] = v[4 + i].y; s.ms[4 * i + 2] = v[4 + i].z; s.ms[4 * i + 3] = v[4 + i].w;
     s.mh[4 * i] = v[6 + i].x; s.mh[4 * i + 1] = v[6 + i].y; s.mh[4 * i + 2] = v[6 + i].z; s.mh[4 * i + 3] = v[6 + i].w;
   }
-  s.ex[0] = __float_as_int(v[8].x); s.ex[1] = __float_as_int(v[8].y);
-  s.ex[2] = __float_as_int(v[8].z); s.ex[3] = __float_as_int(v[8].w);
-  s.ex[4] = __float_as_int(v[9].x); s.ex[5] = __float_as_int(v[9].y);
-  s.ex[6] = __float_as_int(v[9].z); s.ex[7] = __float_as_int(v[9].w);
-  s.ex[8] = __float_as_int(v[10].x);
-  s.en0 = (unsigned)__float_as_int(v[10].y);
-  s.en1 = (unsigned)__float_as_int(v[10].z);
-  s.all_jump = __float_as_int(v[10].w);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    s.soff[4 * i] = __float_as_int(v[8 + i].x); s.soff[4 * i + 1] = __float_as_int(v[8 + i].y);
+    s.soff[4 * i + 2] = __float_as_int(v[8 + i].z); s.soff[4 * i + 3] = __float_as_int(v[8 + i].w);
+  }
+  s.all_jump = __float_as_int(v[12].x);
 }
 
-// Add rw * (emitted cell values) into one plane row.  All enabled cells are distinct, so
-// the loads are issued together, then the stores.  ALLJ: every one of the 16 cells is enabled.
+// predicated (branch-free) shared-memory access: active iff off >= 0
+__device__ __forceinline__ float lds_if(unsigned addr, int off) {
+  float v = 0.f;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %2, 0;\n\t@p ld.shared.f32 %0, [%1];\n\t}"
+               : "+f"(v) : "r"(addr), "r"(off));
+  return v;
+}
+__device__ __forceinline__ void sts_if(unsigned addr, int off, float v) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %2, 0;\n\t@p st.shared.f32 [%1], %0;\n\t}"
+               :: "f"(v), "r"(addr), "r"(off) : "memory");
+}
+__device__ __forceinline__ void sts_f32(unsigned addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" :: "r"(addr), "f"(v) : "memory");
+}
+
+// Add rw0 * e into plane row y0 and rw1 * e into row y0 + 1 (rows outside the band have
+// do0 / do1 false).  e[j] is the value of site j.  All enabled cells of a row are distinct,
+// so all loads are issued first, then the stores.  ALLJ: all 16 sites are enabled.
 template <bool ALLJ>
-__device__ __forceinline__ void bw_rmw_row(float* __restrict__ row, float rw, const BwdState& s,
-                                           const float (&e0)[9], const float (&e1)[9]) {
-  float o0[9], o1[9];
+__device__ __forceinline__ void bw_rmw_rows(unsigned row0, unsigned row1, bool do0, bool do1, float rw0,
+                                            float rw1, const BwdState& s, const float (&e)[16]) {
+  float o0[16], o1[16];
+  if (do0) {
 #pragma unroll
-  for (int t = 1; t <= 8; ++t) {
-    o0[t] = (ALLJ || ((s.en0 >> t) & 1u)) ? row[s.ex[t]] : 0.f;
-    o1[t] = (ALLJ || ((s.en1 >> t) & 1u)) ? row[s.ex[t] + 1] : 0.f;
+    for (int j = 0; j < 16; ++j)
+      o0[j] = ALLJ ? lds_f32(row0 + (unsigned)s.soff[j]) : lds_if(row0 + (unsigned)s.soff[j], s.soff[j]);
   }
+  if (do1) {
 #pragma unroll
-  for (int t = 1; t <= 8; ++t) {
-    if (ALLJ || ((s.en0 >> t) & 1u)) row[s.ex[t]] = fmaf(rw, e0[t], o0[t]);
-    if (ALLJ || ((s.en1 >> t) & 1u)) row[s.ex[t] + 1] = fmaf(rw, e1[t], o1[t]);
+    for (int j = 0; j < 16; ++j)
+      o1[j] = ALLJ ? lds_f32(row1 + (unsigned)s.soff[j]) : lds_if(row1 + (unsigned)s.soff[j], s.soff[j]);
+  }
+  if (do0) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float v = fmaf(rw0, e[j], o0[j]);
+      if (ALLJ) sts_f32(row0 + (unsigned)s.soff[j], v); else sts_if(row0 + (unsigned)s.soff[j], s.soff[j], v);
+    }
+  }
+  if (do1) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float v = fmaf(rw1, e[j], o1[j]);
+      if (ALLJ) sts_f32(row1 + (unsigned)s.soff[j], v); else sts_if(row1 + (unsigned)s.soff[j], s.soff[j], v);
+    }
   }
 }
 
-__device__ __forceinline__ void bw_item(float* __restrict__ plane, int W, int y_lo, int y_hi,
+__device__ __forceinline__ void bw_item(unsigned plane_addr, int W, int y_lo, int y_hi,
                                         const float (&g)[8], const float4 rowt, const BwdState& s) {
-  float e0[9], e1[9];
+  float e[16];
   const int y0 = __float_as_int(rowt.w);
   const bool in0 = y0 >= y_lo && y0 < y_hi, in1 = y0 + 1 >= y_lo && y0 + 1 < y_hi;
+  const unsigned row0 = plane_addr + 4u * (unsigned)((y0 - y_lo) * W);
+  const unsigned row1 = row0 + 4u * (unsigned)W;
   if (s.all_jump) {
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
-      e0[t + 1] = g[t] * s.cw0[t];
-      e1[t + 1] = g[t] * s.cw1[t];
+      e[2 * t] = g[t] * s.cw0[t];
+      e[2 * t + 1] = g[t] * s.cw1[t];
     }
-    if (in0) bw_rmw_row<true>(plane + (y0 - y_lo) * W, rowt.y, s, e0, e1);
-    if (in1) bw_rmw_row<true>(plane + (y0 + 1 - y_lo) * W, rowt.z, s, e0, e1);
+    bw_rmw_rows<true>(row0, row1, in0, in1, rowt.y, rowt.z, s, e);
   } else {
     float a0 = 0.f, a1 = 0.f;
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
-      if (t > 0) { e0[t] = a0; e1[t] = a1; }
+      if (t > 0) { e[2 * (t - 1)] = a0; e[2 * (t - 1) + 1] = a1; }
       const float na0 = fmaf(s.ms[t], a0, fmaf(s.mh[t], a1, g[t] * s.cw0[t]));
       a1 = fmaf(s.ms[t], a1, g[t] * s.cw1[t]);
       a0 = na0;
     }
-    e0[8] = a0; e1[8] = a1;
-    if (in0) bw_rmw_row<false>(plane + (y0 - y_lo) * W, rowt.y, s, e0, e1);
-    if (in1) bw_rmw_row<false>(plane + (y0 + 1 - y_lo) * W, rowt.z, s, e0, e1);
+    e[14] = a0; e[15] = a1;
+    bw_rmw_rows<false>(row0, row1, in0, in1, rowt.y, rowt.z, s, e);
   }
 }
 
@@ -661,7 +703,7 @@ __global__ void __launch_bounds__(BW_THREADS)
   const int cw = grp * BW_CH + wid * 32;       // first channel of this consumer warp
   const bool active = !producer && cw < C;     // C % 32 == 0
   const int n_active = min(BW_WARPS, (C - grp * BW_CH) / 32);
-  float* plane = planes + (size_t)((wid & (BW_WARPS - 1)) * 32 + lane) * Sb;
+  const unsigned plane_addr = smem_u32(planes + (size_t)((wid & (BW_WARPS - 1)) * 32 + lane) * Sb);
 
   if (tid == 0) {
     for (int s = 0; s < BW_STAGES; ++s) {
@@ -725,10 +767,13 @@ __global__ void __launch_bounds__(BW_THREADS)
           const int s = it % BW_STAGES;
           const unsigned ph = (it / BW_STAGES) & 1u;
           mbar_wait(&sh.empty_bar[s], ph ^ 1u);
-          mbar_arrive_expect_tx(&sh.full_bar[s], BW_STAGE_BYTES);
+          mbar_arrive_expect_tx(&sh.full_bar[s], BW_TILE_BYTES + (unsigned)sizeof(BwdCols) + 16u);
           const int item = sh.items[i];
-          tma_load_4d(stages + s * BW_STAGE_BYTES, &tmap, &sh.full_bar[s], 0, item & 15, grp * BW_CH,
-                      item >> 4);
+          unsigned char* stg = stages + s * BW_STAGE_BYTES;
+          tma_load_4d(stg, &tmap, &sh.full_bar[s], 0, item & 15, grp * BW_CH, item >> 4);
+          bulk_load(stg + BW_TILE_BYTES, pl.bwdx + (item >> 4), (unsigned)sizeof(BwdCols), &sh.full_bar[s]);
+          bulk_load(stg + BW_TILE_BYTES + sizeof(BwdCols), pl.tabs + (size_t)(item >> 4) * 32 + (item & 15),
+                    16u, &sh.full_bar[s]);
         }
       }
     } else if (active) {
@@ -739,18 +784,18 @@ __global__ void __launch_bounds__(BW_THREADS)
       for (int i = 0; i < nitems; ++i) {
         const unsigned it = it0 + (unsigned)i;
         const int s = it % BW_STAGES;
-        const int item = sh.items[i];
-        const int nn = item >> 4;
-        if (nn != st.n) { bw_load_cols(st, pl.bwdx + nn); st.n = nn; }
-        const float4 rowt = __ldg(pl.tabs + (size_t)nn * 32 + (item & 15));
+        const int nn = sh.items[i] >> 4;
         mbar_wait(&sh.full_bar[s], (it / BW_STAGES) & 1u);
-        const unsigned char* tile = stages + s * BW_STAGE_BYTES + r * 32;
-        const float4 ga = *reinterpret_cast<const float4*>(tile + sw);
-        const float4 gb = *reinterpret_cast<const float4*>(tile + (sw ^ 16));
+        const unsigned char* stg = stages + s * BW_STAGE_BYTES;
+        const float4 ga = *reinterpret_cast<const float4*>(stg + r * 32 + sw);
+        const float4 gb = *reinterpret_cast<const float4*>(stg + r * 32 + (sw ^ 16));
+        const float4* meta = reinterpret_cast<const float4*>(stg + BW_TILE_BYTES);
+        const float4 rowt = meta[13];
+        if (nn != st.n) { bw_load_cols(st, meta); st.n = nn; }
         __syncwarp();
         if (lane == 0) mbar_arrive(&sh.empty_bar[s]);
         const float g[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
-        bw_item(plane, W, y_lo, y_hi, g, rowt, st);
+        bw_item(plane_addr, W, y_lo, y_hi, g, rowt, st);
       }
     }
     it0 += (unsigned)nitems;
