@@ -135,7 +135,9 @@ int tlod_roi_pool_backward(const float* top_grad, const int* argmax, const float
  * keep_out[0 .. *num_out) = ascending kept indices, both on the DEVICE; no host
  * synchronisation happens inside (the reference does 4).  max_keep > 0 stops
  * after that many survivors (the caller's `[:post_nms_topN]`).
- * workspace: tlod_nms_workspace_bytes(n) bytes, 16-byte aligned. */
+ * The IoU mask is only computed for the leading boxes the scan can reach before max_keep
+ * survivors exist (extended x4 on demand), so a small max_keep makes the call much cheaper.
+ * workspace: tlod_nms_workspace_bytes(n) bytes, 32-byte aligned. */
 size_t tlod_nms_workspace_bytes(int n);
 int tlod_nms(const float* boxes, int n, int box_stride, float thresh, int max_keep, int* keep_out,
              int* num_out, void* workspace, size_t workspace_bytes, void* stream);

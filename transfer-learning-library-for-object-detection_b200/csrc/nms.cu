@@ -6,15 +6,17 @@
 //   proposal layer lib/model/rpn/proposal_layer.py:49-163,
 //                  lib/model/rpn/bbox_transform.py:77-103 (decode), :125-133 (clip)
 //
-// Pipeline for a batch (3 launches, no host synchronisation, no D2H mask copy):
-//   1. proposal_topk_decode_kernel  one CTA per image: 64-bit radix select of the
-//      pre_nms_topN best (score desc, index asc) keys, bitonic sort in shared
-//      memory, decode + clip of only the selected anchors.
-//   2. nms_mask_kernel              upper-triangular 64x64 tiles of the IoU > thresh
-//      bitmask over all images (fp32 ALU bound; this is where the time goes).
-//   3. nms_scan_kernel              one CTA per image: the greedy scan the reference
-//      runs on the host, done on chip with a speculative prefetch of the diagonal
-//      and super-diagonal mask words, then the padded (post_nms_topN, 5) output.
+// Pipeline for a batch (no host synchronisation, no D2H mask copy):
+//   1. proposal_sort_runs_kernel + proposal_rank_decode_kernel: sort by ranking of the
+//      (score desc, index asc) keys over many CTAs; only the pre_nms_topN best anchors are
+//      decoded + clipped, each written straight to its rank.
+//   2. nms_mask_kernel   upper-triangular 64x64 tiles of the IoU > thresh bitmask (fp32 ALU
+//      bound), computed in phases: only the leading S x S triangle the scan can reach before
+//      post_nms_topN boxes have survived, extended x4 only if the scan asks for it.
+//   3. nms_scan_kernel   one CTA per image: the greedy scan the reference runs on the host,
+//      done on chip: each 64-box chunk is resolved in a few warp-wide rounds, with a
+//      speculative prefetch of the diagonal and super-diagonal mask words; then the padded
+//      (post_nms_topN, 5) output.
 #include "common.cuh"
 
 namespace tlod {
@@ -58,45 +60,97 @@ __device__ __forceinline__ float4 load_box(const float* __restrict__ p, int stri
   return make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
 }
 
-// grid (col_blocks, row_blocks, batch); 64 threads; only col_block >= row_block does work.
+// Words per mask row: the column blocks, padded to a multiple of 4 so that every row starts on
+// a 32-byte sector and the scan can fetch four words per load.
+__host__ __device__ inline int nms_row_words(int n) { return (((n + 63) >> 6) + 3) & ~3; }
+
+// Per-image scan state carried from one phase to the next.
+struct NmsState {
+  int nkeep;  // survivors so far (<= max_keep)
+  int done;   // max_keep reached or every box examined: later phases exit at once
+};
+
+// Phase p covers the boxes [S_{p-1}, S_p).  Its mask kernel fills, for the column blocks of
+// the phase, the 64x64 tiles of all row blocks at or above the diagonal; the scan kernel then
+// continues the greedy scan over those boxes.  S_1 is sized so that the scan normally reaches
+// max_keep inside phase 1 (the IoU work is then S_1^2/2 pairs instead of n^2/2); if it does
+// not, the next phase is four times larger.  Later phases find `done` set and return.
+__host__ __device__ inline int nms_phase_end(int n, int max_keep, int phase /* 1-based */) {
+  long long s = 2LL * max_keep;
+  if (s < 1024) s = 1024;
+  s = (s + 63) / 64 * 64;
+  for (int p = 1; p < phase && s < n; ++p) s *= 4;
+  return s < n ? (int)s : n;
+}
+
+// Persistent grid (gridDim.x CTAs per image, blockIdx.y = image); 256 threads: thread t owns
+// row t >> 2 of a 64x64 tile and 16 of its 64 columns.  The tiles of a phase are the pairs
+// (col block cb in [cb0, cb1), row block rb <= cb), numbered cb-major.
 // mask[(img * n + row) * ncb + col_block], bits for columns > row only.
 template <bool FILTER>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(256)
     nms_mask_kernel(const float* __restrict__ boxes, int n, int stride, float thresh,
-                    unsigned long long* __restrict__ mask) {
-  const int col_blk = blockIdx.x, row_blk = blockIdx.y, img = blockIdx.z;
-  if (col_blk < row_blk) return;
-  const int ncb = gridDim.x;
+                    unsigned long long* __restrict__ mask, int rs, int cb0, int cb1, int first_phase,
+                    NmsState* __restrict__ state) {
+  const int img = blockIdx.y;
+  const int t = threadIdx.x;
+  if (first_phase) {
+    if (blockIdx.x == 0 && t == 0) {
+      state[img].nkeep = 0;
+      state[img].done = 0;
+    }
+  } else if (state[img].done) {
+    return;
+  }
   const float* bx = boxes + (size_t)img * n * stride;
   __shared__ float4 cbox[64];
   __shared__ float carea[64];
-  const int col_size = min(n - col_blk * 64, 64);
-  const int row_size = min(n - row_blk * 64, 64);
-  const int t = threadIdx.x;
-  if (t < col_size) {
-    const float4 b = load_box(bx + (size_t)(col_blk * 64 + t) * stride, stride);
-    cbox[t] = b;
-    carea[t] = box_area(b);
-  }
-  __syncthreads();
-  if (t >= row_size) return;
-  const int row = row_blk * 64 + t;
-  const float4 a = load_box(bx + (size_t)row * stride, stride);
-  const float area_a = box_area(a);
   const float thr_hi = thresh * (1.f + 9.5367431640625e-7f);
   const float thr_lo = thresh * (1.f - 9.5367431640625e-7f);
-  unsigned long long bits = 0;
+  const long long tri0 = (long long)cb0 * (cb0 + 1) / 2;
+  const long long ntiles = (long long)cb1 * (cb1 + 1) / 2 - tri0;
+  const int r = t >> 2, q = t & 3;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // tile + tri0 = cb (cb + 1) / 2 + rb, 0 <= rb <= cb
+    const long long g = tile + tri0;
+    int col_blk = (int)((sqrtf(8.f * (float)g + 1.f) - 1.f) * 0.5f);
+    while ((long long)col_blk * (col_blk + 1) / 2 > g) --col_blk;
+    while ((long long)(col_blk + 1) * (col_blk + 2) / 2 <= g) ++col_blk;
+    const int row_blk = (int)(g - (long long)col_blk * (col_blk + 1) / 2);
+    const int col_size = min(n - col_blk * 64, 64);
+    const int row_size = min(n - row_blk * 64, 64);
+    __syncthreads();  // previous tile's cbox readers
+    if (t < col_size) {
+      const float4 b = load_box(bx + (size_t)(col_blk * 64 + t) * stride, stride);
+      cbox[t] = b;
+      carea[t] = box_area(b);
+    }
+    __syncthreads();
+    const int row = row_blk * 64 + (r < row_size ? r : 0);
+    const float4 a = load_box(bx + (size_t)row * stride, stride);
+    const float area_a = box_area(a);
+    unsigned bits = 0;
 #pragma unroll 8
-  for (int j = 0; j < col_size; ++j) {
-    if (box_suppresses<FILTER>(a, area_a, cbox[j], carea[j], thresh, thr_hi, thr_lo))
-      bits |= 1ULL << j;
+    for (int j = 0; j < 16; ++j) {
+      const int c = q * 16 + j;
+      if (c < col_size && box_suppresses<FILTER>(a, area_a, cbox[c], carea[c], thresh, thr_hi, thr_lo))
+        bits |= 1u << j;
+    }
+    // assemble the 64-bit word of the row from its four 16-bit quarters (adjacent lanes)
+    unsigned lo = (q == 0) ? bits : (q == 1 ? bits << 16 : 0u);
+    unsigned hi = (q == 2) ? bits : (q == 3 ? bits << 16 : 0u);
+    lo |= __shfl_xor_sync(0xffffffffu, lo, 1); hi |= __shfl_xor_sync(0xffffffffu, hi, 1);
+    lo |= __shfl_xor_sync(0xffffffffu, lo, 2); hi |= __shfl_xor_sync(0xffffffffu, hi, 2);
+    if (q == 0 && r < row_size) {
+      unsigned long long w = ((unsigned long long)hi << 32) | lo;
+      if (row_blk == col_blk) w &= ~((2ULL << r) - 1ULL);  // keep columns > row only
+      mask[((size_t)img * n + row) * rs + col_blk] = w;
+    }
   }
-  if (row_blk == col_blk) bits &= ~((2ULL << t) - 1ULL);  // keep columns > row only
-  mask[((size_t)img * n + row) * ncb + col_blk] = bits;
 }
 
 // ===========================================================================
-// greedy scan (one CTA per image)
+// greedy scan (one CTA per image and phase)
 // ===========================================================================
 constexpr int SCAN_THREADS = 256;
 
@@ -135,6 +189,31 @@ __device__ __forceinline__ unsigned long long or_rows(const unsigned long long* 
   return acc;
 }
 
+// Greedy resolve of one 64-box chunk inside a warp.  `cand` = boxes not suppressed from
+// outside the chunk; d0 / d1 = this lane's rows (lane, lane + 32) of the diagonal block
+// (bits above the row index only).  Instead of one step per survivor, every round keeps ALL
+// undecided boxes that no earlier undecided box suppresses (the lowest one always
+// qualifies) and removes their victims; the result equals the sequential scan
+// (nms_cuda_kernel.cu:132-144) and the number of rounds is the longest suppression chain.
+__device__ __forceinline__ unsigned long long resolve_chunk(unsigned long long cand,
+                                                            unsigned long long d0,
+                                                            unsigned long long d1, int lane) {
+  unsigned long long und = cand, kept = 0ULL;
+  while (und) {
+    unsigned long long t = 0ULL;
+    if ((und >> lane) & 1ULL) t |= d0;
+    if ((und >> (lane + 32)) & 1ULL) t |= d1;
+    const unsigned long long safe = und & ~warp_or_u64(t);
+    kept |= safe;
+    unsigned long long v = 0ULL;
+    if ((safe >> lane) & 1ULL) v |= d0;
+    if ((safe >> (lane + 32)) & 1ULL) v |= d1;
+    und &= ~(safe | warp_or_u64(v));
+  }
+  return kept;
+}
+
+// Continues the scan over the chunks [c0, c1) of one phase.
 // keep_out[img * keep_stride + r] = r-th kept index (ascending), num_out[img] = count
 // (<= max_keep).  If rois_out != NULL also writes the reference's padded
 // (post, 5) block for the image: column 0 = image index, rows [0, count) = boxes.
@@ -144,56 +223,70 @@ __device__ __forceinline__ unsigned long long or_rows(const unsigned long long* 
 //     remv[c]                      rows of survivors of chunks <= c-3   (other warps, below)
 //   | OR survivors(c-1) of mask[row][c]   "s1", prefetched by warp 0 before it knew the survivors
 //   | OR survivors(c-2) of mask[row][c]   "s2", likewise
-// so the only serial work per chunk is the in-register resolve of the 64x64 diagonal block.
 // The other 7 warps fold the rows of chunk c's survivors into remv[j >= c+3]; their loads are
 // issued in iteration c and consumed in iteration c+1, two barriers before warp 0 needs them.
 __global__ void __launch_bounds__(SCAN_THREADS)
     nms_scan_kernel(const unsigned long long* __restrict__ mask, int n, int max_keep,
                     int* __restrict__ keep_out, int keep_stride, int* __restrict__ num_out,
                     const float* __restrict__ boxes, int box_stride, float* __restrict__ rois_out,
-                    int post) {
-  extern __shared__ unsigned long long remv[];  // ncb words
+                    int post, int c0, int c1, int last_phase, NmsState* __restrict__ state, int rs) {
+  extern __shared__ unsigned long long remv[];  // ncb words (only [c0, c1) are used)
   __shared__ unsigned long long kept_sh[2];
   __shared__ int done_sh[2];
-  constexpr int HELPERS = SCAN_THREADS - 32;
+  __shared__ int nkeep_sh;
   const int img = blockIdx.x;
-  const int ncb = (n + 63) >> 6;
-  const unsigned long long* m = mask + (size_t)img * n * ncb;
+  if (state[img].done) return;
+  const unsigned long long* m = mask + (size_t)img * n * rs;
   int* keep = keep_out + (size_t)img * keep_stride;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  for (int j = tid; j < ncb; j += SCAN_THREADS) remv[j] = 0ULL;
+  const int nkeep0 = state[img].nkeep;
+
+  // ---- carry-in: rows of the survivors of earlier phases, at the words of this phase ----
+  for (int j = c0 + wid; j < c1; j += SCAN_THREADS / 32) {
+    unsigned long long acc = 0ULL;
+    for (int k = lane; k < nkeep0; k += 32 * 4) {
+      unsigned long long v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = (k + 32 * u < nkeep0) ? m[(size_t)keep[k + 32 * u] * rs + j] : 0ULL;
+      acc |= v[0] | v[1] | v[2] | v[3];
+    }
+    acc = warp_or_u64(acc);
+    if (lane == 0) remv[j] = acc;
+  }
   __syncthreads();
 
   // ---- warp 0 state ----
-  int nkeep = 0;
+  int nkeep = nkeep0;
   unsigned long long d0 = 0, d1 = 0;      // diagonal words of the current chunk (rows lane, lane+32)
   unsigned long long s1a = 0, s1b = 0;    // rows of chunk c-1 at word c
   unsigned long long s2a = 0, s2b = 0;    // rows of chunk c-2 at word c
-  unsigned long long kept1 = 0ULL, kept2 = 0ULL;  // survivors of chunks c-1, c-2
-  if (wid == 0 && ncb > 0) {
-    if (lane < n) d0 = m[(size_t)lane * ncb];
-    if (lane + 32 < n) d1 = m[(size_t)(lane + 32) * ncb];
+  unsigned long long kept1 = 0ULL, kept2 = 0ULL;  // survivors of chunks c-1, c-2 (this phase)
+  if (wid == 0 && c0 < c1) {
+    if (64 * c0 + lane < n) d0 = m[(size_t)(64 * c0 + lane) * rs + c0];
+    if (64 * c0 + lane + 32 < n) d1 = m[(size_t)(64 * c0 + lane + 32) * rs + c0];
   }
-  // ---- helper state: word owned this round and its loads in flight ----
-  int pend_j = -1;
-  unsigned long long pend[8];
-#pragma unroll
-  for (int u = 0; u < 8; ++u) pend[u] = 0ULL;
-
-  for (int c = 0; c < ncb; ++c) {
+  // ---- helper state: loads in flight (issued in iteration c, folded in iteration c + 1) ----
+  // Helper warp h (1..7) owns the groups of four consecutive words (one 32-byte sector per
+  // mask row) g = h - 1, h - 1 + 7, ...; lane l loads the sectors of rows l and l + 32 of the
+  // chunk if those boxes survived.
+  constexpr int HW = SCAN_THREADS / 32 - 1;  // helper warps
+  constexpr int MAXG = 4;                    // word groups per helper warp kept in flight
+  ulonglong4 pend[MAXG][2];
+  int pend_c = -1;
+  for (int c = c0; c < c1; ++c) {
     if (wid == 0) {
       // prefetch everything chunk c+1 will need that does not depend on decisions
       unsigned long long nd0 = 0, nd1 = 0, n1a = 0, n1b = 0, n2a = 0, n2b = 0;
-      if (c + 1 < ncb) {  // then chunks <= c are full: all their rows exist
+      if (c + 1 < c1) {  // then chunks <= c are full: all their rows exist
         const int w1 = c + 1;
         const int r0 = 64 * w1 + lane, r1 = r0 + 32;
-        if (r0 < n) nd0 = m[(size_t)r0 * ncb + w1];
-        if (r1 < n) nd1 = m[(size_t)r1 * ncb + w1];
-        n1a = m[(size_t)(64 * c + lane) * ncb + w1];
-        n1b = m[(size_t)(64 * c + 32 + lane) * ncb + w1];
-        if (c >= 1) {
-          n2a = m[(size_t)(64 * (c - 1) + lane) * ncb + w1];
-          n2b = m[(size_t)(64 * (c - 1) + 32 + lane) * ncb + w1];
+        if (r0 < n) nd0 = m[(size_t)r0 * rs + w1];
+        if (r1 < n) nd1 = m[(size_t)r1 * rs + w1];
+        n1a = m[(size_t)(64 * c + lane) * rs + w1];
+        n1b = m[(size_t)(64 * c + 32 + lane) * rs + w1];
+        if (c >= c0 + 1) {
+          n2a = m[(size_t)(64 * (c - 1) + lane) * rs + w1];
+          n2b = m[(size_t)(64 * (c - 1) + 32 + lane) * rs + w1];
         }
       }
       unsigned long long urgent = 0ULL;
@@ -205,15 +298,7 @@ __global__ void __launch_bounds__(SCAN_THREADS)
       const unsigned long long cur = remv[c] | urgent;
       const int rows = min(64, n - 64 * c);
       const unsigned long long valid = rows == 64 ? ~0ULL : ((1ULL << rows) - 1ULL);
-      unsigned long long alive = ~cur & valid;
-      unsigned long long kept = 0ULL;
-      while (alive) {
-        const int b = __ffsll((long long)alive) - 1;
-        kept |= 1ULL << b;
-        const unsigned long long w = shfl_u64(b < 32 ? d0 : d1, b & 31);
-        alive &= ~w;
-        alive &= ~(1ULL << b);
-      }
+      const unsigned long long kept = resolve_chunk(~cur & valid, d0, d1, lane);
       // emit indices (ascending) up to max_keep
       if ((kept >> lane) & 1ULL) {
         const int r = nkeep + __popcll(kept & ((1ULL << lane) - 1ULL));
@@ -236,46 +321,78 @@ __global__ void __launch_bounds__(SCAN_THREADS)
     __syncthreads();
     if (done_sh[c & 1]) break;
     if (wid != 0) {
-      // consume the loads issued one iteration ago (rows of chunk c-1)
-      if (pend_j >= 0) {
-        unsigned long long acc = 0ULL;
+      const int h = wid - 1;
+      // fold the sectors loaded one iteration ago (rows of chunk pend_c's survivors)
+      if (pend_c >= 0) {
+        const int g0 = (pend_c + 3) >> 2;  // first word group with words >= pend_c + 3
 #pragma unroll
-        for (int u = 0; u < 8; ++u) acc |= pend[u];
-        remv[pend_j] |= acc;
-        pend_j = -1;
-      }
-      // rows of chunk c's survivors -> words j >= c+3.  A word is always handled by the
-      // same thread (j mod HELPERS), so the read-modify-writes of remv never race.
-      unsigned long long k = kept_sh[c & 1];
-      const int t = tid - 32;
-      const int first = c + 3;
-      int j = first + ((t - first) % HELPERS + HELPERS) % HELPERS;
-      if (k && j < ncb) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          pend[u] = 0ULL;
-          if (k) {
-            const int b = __ffsll((long long)k) - 1;
-            k &= k - 1ULL;
-            pend[u] = m[(size_t)(64 * c + b) * ncb + j];
+        for (int u = 0; u < MAXG; ++u) {
+          const int g = g0 + h + u * HW;
+          if (4 * g < c1) {
+            const unsigned long long w0 = warp_or_u64(pend[u][0].x | pend[u][1].x);
+            const unsigned long long w1 = warp_or_u64(pend[u][0].y | pend[u][1].y);
+            const unsigned long long w2 = warp_or_u64(pend[u][0].z | pend[u][1].z);
+            const unsigned long long w3 = warp_or_u64(pend[u][0].w | pend[u][1].w);
+            if (lane == 0) {
+              // words below pend_c + 3 are covered by warp 0's s1 / s2 path or already passed
+              if (4 * g + 0 >= pend_c + 3 && 4 * g + 0 < c1) remv[4 * g + 0] |= w0;
+              if (4 * g + 1 >= pend_c + 3 && 4 * g + 1 < c1) remv[4 * g + 1] |= w1;
+              if (4 * g + 2 >= pend_c + 3 && 4 * g + 2 < c1) remv[4 * g + 2] |= w2;
+              if (4 * g + 3 >= pend_c + 3 && 4 * g + 3 < c1) remv[4 * g + 3] |= w3;
+            }
           }
         }
-        pend_j = j;
-        if (k) remv[j] |= or_rows(m, ncb, 64 * c, j, k);  // more than 8 survivors in the chunk
-        const unsigned long long all = kept_sh[c & 1];
-        for (j += HELPERS; j < ncb; j += HELPERS) remv[j] |= or_rows(m, ncb, 64 * c, j, all);
+        pend_c = -1;
+      }
+      // rows of chunk c's survivors -> words [c+3, c1)
+      const unsigned long long k = kept_sh[c & 1];
+      if (k && c + 3 < c1) {
+        const int g0 = (c + 3) >> 2;
+        const bool s0 = (k >> lane) & 1ULL, s1 = (k >> (lane + 32)) & 1ULL;
+        const ulonglong4 zero = make_ulonglong4(0ULL, 0ULL, 0ULL, 0ULL);
+        const unsigned long long* r0 = m + (size_t)(64 * c + lane) * rs;
+        const unsigned long long* r1 = m + (size_t)(64 * c + lane + 32) * rs;
+#pragma unroll
+        for (int u = 0; u < MAXG; ++u) {
+          const int g = g0 + h + u * HW;
+          pend[u][0] = zero;
+          pend[u][1] = zero;
+          if (4 * g < c1) {
+            if (s0) pend[u][0] = *reinterpret_cast<const ulonglong4*>(r0 + 4 * g);
+            if (s1) pend[u][1] = *reinterpret_cast<const ulonglong4*>(r1 + 4 * g);
+          }
+        }
+        pend_c = c;
+        // phases wider than MAXG * HW * 4 = 112 words: the rest, folded at once
+        for (int g = g0 + h + MAXG * HW; 4 * g < c1; g += HW) {
+          unsigned long long w[4] = {0ULL, 0ULL, 0ULL, 0ULL};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (4 * g + q < c1) {
+              if (s0) w[q] |= r0[4 * g + q];
+              if (s1) w[q] |= r1[4 * g + q];
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const unsigned long long v = warp_or_u64(w[q]);
+            if (lane == 0 && 4 * g + q >= c + 3 && 4 * g + q < c1) remv[4 * g + q] |= v;
+          }
+        }
       }
     }
   }
   __syncthreads();
-  if (tid == 0) {
-    // nkeep lives in warp 0 only
-    num_out[img] = min(nkeep, max_keep);
-    done_sh[0] = min(nkeep, max_keep);
-  }
+  if (tid == 0) nkeep_sh = min(nkeep, max_keep);  // nkeep lives in warp 0 only
   __syncthreads();
-  if (rois_out) {
-    const int cnt = done_sh[0];
+  const int cnt = nkeep_sh;
+  const bool finished = cnt >= max_keep || last_phase;
+  if (tid == 0) {
+    state[img].nkeep = cnt;
+    state[img].done = finished ? 1 : 0;
+    if (finished) num_out[img] = cnt;
+  }
+  if (finished && rois_out) {
     float* o = rois_out + (size_t)img * post * 5;
     const float* bx = boxes + (size_t)img * n * box_stride;
     for (int r = tid; r < post; r += SCAN_THREADS) {
@@ -291,11 +408,18 @@ __global__ void __launch_bounds__(SCAN_THREADS)
 }
 
 // ===========================================================================
-// top-k select + sort + decode (one CTA per image)
+// top-k + sort + decode: sort by ranking
 // ===========================================================================
+// Keys are unique 64-bit composites (~score_key << 32 | flat anchor index): smaller = better
+// (higher score, then lower index = the stable descending sort of proposal_layer.py:125).
+//   1. proposal_sort_runs_kernel: every CTA bitonic-sorts one run of TK_RUN keys in shared
+//      memory and writes it to the workspace.
+//   2. proposal_rank_decode_kernel: every key finds its global rank = its position in its own
+//      run + the number of smaller keys in every other run (binary searches over the
+//      L2-resident runs); if rank < n_sorted the anchor is decoded, clipped and written
+//      straight to row `rank`.  No merge passes, no single-CTA serial section.
 constexpr int TK_THREADS = 1024;
-constexpr int TK_BINS = 2048;
-constexpr int TK_SMEM_SORT = 16384;  // 64-bit keys sortable in shared memory
+constexpr int TK_RUN = 2048;
 
 // Monotone key: larger score -> larger key.  -0 == +0, every NaN sorts first
 // (torch.sort puts NaN first in descending order).
@@ -306,145 +430,160 @@ __device__ __forceinline__ unsigned score_key(float f) {
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
-struct TKShared {
-  int hist[TK_BINS];
-  int warp_sums[TK_THREADS / 32];
-  int found_digit;
-  int found_need;
-  int found_count;
-  int counter;
-  float anchors[64 * 4];
-};
-
-// composite key of flat anchor index i: smaller = better (higher score, then lower index)
-__device__ __forceinline__ unsigned long long comp_key(const float* __restrict__ fg, int K, int A,
-                                                       int mem_idx, int* flat_idx) {
-  const int a = mem_idx / K;
-  const int k = mem_idx - a * K;
-  const int i = k * A + a;
-  *flat_idx = i;
-  const unsigned key = score_key(__ldg(fg + mem_idx));
-  return ((unsigned long long)(~key) << 32) | (unsigned)i;
-}
-
-__device__ inline void bitonic_sort_u64(unsigned long long* buf, int n_pad) {
-  for (int k = 2; k <= n_pad; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = threadIdx.x; t < (n_pad >> 1); t += blockDim.x) {
-        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-        const int l = i | j;
-        const unsigned long long a = buf[i], b = buf[l];
-        const bool up = (i & k) == 0;
-        if ((a > b) == up) {
-          buf[i] = b;
-          buf[l] = a;
-        }
-      }
-      __syncthreads();
-    }
+// Bitonic stages j = jmax .. 1 (jmax <= 32) of merge size k on the two keys (elements 2t and
+// 2t + 1) a thread holds: partners for j >= 2 are in the same warp (lane ^ j/2).
+__device__ __forceinline__ void bitonic_reg_phase(unsigned long long& a, unsigned long long& b, int t,
+                                                  int k, int jmax) {
+  const bool asc = ((2 * t) & k) == 0;
+  for (int j = jmax; j >= 2; j >>= 1) {
+    const unsigned long long pa = __shfl_xor_sync(0xffffffffu, a, j >> 1);
+    const unsigned long long pb = __shfl_xor_sync(0xffffffffu, b, j >> 1);
+    const bool keep_min = (((2 * t) & j) == 0) == asc;
+    a = keep_min ? (a < pa ? a : pa) : (a > pa ? a : pa);
+    b = keep_min ? (b < pb ? b : pb) : (b > pb ? b : pb);
+  }
+  if ((a > b) == asc) {
+    const unsigned long long x = a;
+    a = b;
+    b = x;
   }
 }
 
-// scores (B, 2A, H, W); deltas (B, 4A, H, W); boxes_out (B, n_sorted, 4).
-// gbuf: global scratch (B, n_pad) u64, used only when n_pad > TK_SMEM_SORT.
-__global__ void __launch_bounds__(TK_THREADS, 1)
-    proposal_topk_decode_kernel(const float* __restrict__ scores, const float* __restrict__ deltas,
-                                const float* __restrict__ im_info,
-                                const float* __restrict__ anchors, int A, int H, int W,
-                                int feat_stride, int n_sorted, int n_pad,
-                                unsigned long long* __restrict__ gbuf,
-                                float* __restrict__ boxes_out, int* __restrict__ order_out) {
-  extern __shared__ __align__(16) unsigned char tk_smem[];
-  TKShared& sh = *reinterpret_cast<TKShared*>(tk_smem);
-  unsigned long long* sbuf = reinterpret_cast<unsigned long long*>(tk_smem + sizeof(TKShared));
-  const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int K = H * W, N = K * A;
+// scores (B, 2A, H, W) -> runs (B, nruns, TK_RUN) sorted ascending, padded with ~0.
+// Stages with j <= 32 run in registers / shuffles; only the 15 stages with j >= 64 go through
+// shared memory.
+__global__ void __launch_bounds__(TK_THREADS)
+    proposal_sort_runs_kernel(const float* __restrict__ scores, int A, int K,
+                              unsigned long long* __restrict__ runs) {
+  static_assert(TK_RUN == 2 * TK_THREADS, "two keys per thread");
+  __shared__ unsigned long long buf[TK_RUN];
+  const int run = blockIdx.x, img = blockIdx.y, t = threadIdx.x;
+  const int N = K * A;
   const float* fg = scores + ((size_t)img * 2 * A + A) * K;  // channels [A, 2A)
-  unsigned long long* buf = (n_pad <= TK_SMEM_SORT) ? sbuf : gbuf + (size_t)img * n_pad;
-
-  for (int i = tid; i < A * 4; i += TK_THREADS) sh.anchors[i] = __ldg(anchors + i);
-
-  // ---- 64-bit radix select: threshold `thr` with exactly n_sorted keys <= thr ----
-  unsigned long long thr = ~0ULL;
-  if (n_sorted < N) {
-    unsigned long long prefix = 0ULL;  // value of the bits above the current digit
-    int need = n_sorted;
-    const int shifts[5] = {53, 42, 32, 11, 0};
-    const int widths[5] = {11, 11, 10, 11, 11};
-    int top = 64;  // bits [top, 64) are fixed to `prefix`
-    bool finished = false;
-    for (int pass = 0; pass < 5 && !finished; ++pass) {
-      const int shift = shifts[pass], bits = widths[pass];
-      if (pass == 3) {
-        // bits [22, 32) of the index half are zero for every key (N < 2^22)
-        prefix <<= 10;
-        top = 22;
-      }
-      for (int i = tid; i < TK_BINS; i += TK_THREADS) sh.hist[i] = 0;
-      __syncthreads();
-      for (int mi = tid; mi < N; mi += TK_THREADS) {
-        int fi;
-        const unsigned long long ck = comp_key(fg, K, A, mi, &fi);
-        if (top == 64 || (ck >> top) == prefix) atomicAdd(&sh.hist[(ck >> shift) & ((1u << bits) - 1u)], 1);
-      }
-      __syncthreads();
-      // ascending scan over bins: 2 bins per thread
-      const int b0 = 2 * tid, b1 = 2 * tid + 1;
-      const int h0 = sh.hist[b0], h1 = sh.hist[b1];
-      int incl = h0 + h1;
-      for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += t;
-      }
-      if (lane == 31) sh.warp_sums[wid] = incl;
-      __syncthreads();
-      int before = incl - (h0 + h1);
-      for (int w = 0; w < wid; ++w) before += sh.warp_sums[w];
-      if (before < need && before + h0 >= need) {
-        sh.found_digit = b0; sh.found_need = need - before; sh.found_count = h0;
-      } else if (before + h0 < need && before + h0 + h1 >= need) {
-        sh.found_digit = b1; sh.found_need = need - before - h0; sh.found_count = h1;
-      }
-      __syncthreads();
-      const int digit = sh.found_digit;
-      need = sh.found_need;
-      prefix = (prefix << bits) | (unsigned long long)digit;
-      top = shift;
-      if (sh.found_count == need || shift == 0) {
-        // every key with this prefix is taken: threshold = prefix followed by ones
-        thr = (shift == 0) ? prefix : ((prefix << shift) | ((1ULL << shift) - 1ULL));
-        finished = true;
+  unsigned long long key[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int mi = run * TK_RUN + 2 * t + e;  // memory order: a * K + k
+    key[e] = ~0ULL;
+    if (mi < N) {
+      const int a = mi / K, k = mi - a * K;
+      key[e] = ((unsigned long long)(~score_key(__ldg(fg + mi))) << 32) | (unsigned)(k * A + a);
+    }
+  }
+  unsigned long long a = key[0], b = key[1];
+  for (int k = 2; k <= 64; k <<= 1) bitonic_reg_phase(a, b, t, k, k >> 1);
+  buf[2 * t] = a;
+  buf[2 * t + 1] = b;
+  __syncthreads();
+  for (int k = 128; k <= TK_RUN; k <<= 1) {
+    for (int j = k >> 1; j >= 64; j >>= 1) {
+      const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+      const int l = i | j;
+      const unsigned long long x = buf[i], y = buf[l];
+      if ((x > y) == ((i & k) == 0)) {
+        buf[i] = y;
+        buf[l] = x;
       }
       __syncthreads();
     }
-  }
-
-  // ---- compaction (order is irrelevant: keys are unique and get sorted) ----
-  if (tid == 0) sh.counter = 0;
-  __syncthreads();
-  for (int mi = tid; mi < N; mi += TK_THREADS) {
-    int fi;
-    const unsigned long long ck = comp_key(fg, K, A, mi, &fi);
-    if (ck <= thr) {
-      const int pos = atomicAdd(&sh.counter, 1);
-      if (pos < n_pad) buf[pos] = ck;
+    a = buf[2 * t];
+    b = buf[2 * t + 1];
+    bitonic_reg_phase(a, b, t, k, 32);
+    if (k < TK_RUN) {
+      buf[2 * t] = a;
+      buf[2 * t + 1] = b;
+      __syncthreads();
     }
   }
-  for (int i = n_sorted + tid; i < n_pad; i += TK_THREADS) buf[i] = ~0ULL;
-  __syncthreads();
-  bitonic_sort_u64(buf, n_pad);
+  unsigned long long* out = runs + ((size_t)img * gridDim.x + run) * TK_RUN;
+  reinterpret_cast<ulonglong2*>(out)[t] = make_ulonglong2(a, b);
+}
 
-  // ---- decode + clip only the selected anchors (bbox_transform.py:77-103, :125-133) ----
+// number of keys < key in a sorted run of TK_RUN keys (keys are unique)
+__device__ __forceinline__ int run_lower_bound(const unsigned long long* __restrict__ r,
+                                               unsigned long long key) {
+  int lo = 0;
+#pragma unroll
+  for (int step = TK_RUN / 2; step > 0; step >>= 1)
+    if (__ldg(r + lo + step - 1) < key) lo += step;
+  return lo + (__ldg(r + lo) < key ? 1 : 0);
+}
+
+// Same count with the first 6 of the 11 steps served from shared memory: smp[b] = last key of
+// the b-th block of 32 keys of the run.
+constexpr int TK_SMP = TK_RUN / 32;  // samples per run
+constexpr int TK_SMP_RUNS = 64;      // runs whose samples fit the shared-memory table
+__device__ __forceinline__ int run_lower_bound_2level(const unsigned long long* __restrict__ r,
+                                                      const unsigned long long* __restrict__ smp,
+                                                      unsigned long long key) {
+  int blk = 0;  // number of blocks whose last key is < key
+#pragma unroll
+  for (int step = TK_SMP / 2; step > 0; step >>= 1)
+    if (smp[blk + step - 1] < key) blk += step;
+  blk += (smp[blk] < key) ? 1 : 0;
+  if (blk == TK_SMP) return TK_RUN;
+  const unsigned long long* q = r + blk * 32;
+  int lo = 0;  // keys of the block that are < key (its last key is >= key)
+#pragma unroll
+  for (int step = 16; step > 0; step >>= 1)
+    if (__ldg(q + lo + step - 1) < key) lo += step;
+  return blk * 32 + lo;
+}
+
+// grid (2 * nruns, batch): one key per thread.
+__global__ void __launch_bounds__(TK_THREADS)
+    proposal_rank_decode_kernel(const unsigned long long* __restrict__ runs,
+                                const float* __restrict__ deltas, const float* __restrict__ im_info,
+                                const float* __restrict__ anchors, int A, int H, int W, int feat_stride,
+                                int n_sorted, float* __restrict__ boxes_out, int* __restrict__ order_out) {
+  __shared__ float sh_anchors[64 * 4];
+  __shared__ unsigned long long smp[TK_SMP_RUNS * TK_SMP];
+  const int run = blockIdx.x >> 1, img = blockIdx.y, tid = threadIdx.x, nruns = gridDim.x >> 1;
+  const int K = H * W;
+  const unsigned long long* base = runs + (size_t)img * nruns * TK_RUN;
+  const int p = (blockIdx.x & 1) * TK_THREADS + tid;
+  if ((blockIdx.x & 1) * TK_THREADS >= n_sorted) return;  // whole CTA: rank >= p >= n_sorted
+  for (int i = tid; i < A * 4; i += TK_THREADS) sh_anchors[i] = __ldg(anchors + i);
+  const bool two_level = nruns <= TK_SMP_RUNS;
+  if (two_level)
+    for (int i = tid; i < nruns * TK_SMP; i += TK_THREADS)
+      smp[i] = __ldg(base + (size_t)(i / TK_SMP) * TK_RUN + (i % TK_SMP) * 32 + 31);
+  __syncthreads();
   const float im_h = __ldg(im_info + img * 3 + 0), im_w = __ldg(im_info + img * 3 + 1);
   const float max_x = __fsub_rn(im_w, 1.f), max_y = __fsub_rn(im_h, 1.f);
   const float* dl = deltas + (size_t)img * 4 * A * K;
-  for (int r = tid; r < n_sorted; r += TK_THREADS) {
-    const int i = (int)(unsigned)buf[r];
+  {
+    if (p >= n_sorted) return;  // rank >= p
+    const unsigned long long key = __ldg(base + (size_t)run * TK_RUN + p);
+    if (key == ~0ULL) return;   // padding
+    int rank = p;
+    if (two_level) {
+      // independent searches, eight in flight
+      int r2 = 0;
+      for (; r2 + 8 <= nruns; r2 += 8) {
+        int c[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          c[u] = (r2 + u == run) ? 0
+                                 : run_lower_bound_2level(base + (size_t)(r2 + u) * TK_RUN,
+                                                          smp + (r2 + u) * TK_SMP, key);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) rank += c[u];
+      }
+      for (; r2 < nruns; ++r2)
+        if (r2 != run) rank += run_lower_bound_2level(base + (size_t)r2 * TK_RUN, smp + r2 * TK_SMP, key);
+    } else {
+      for (int r2 = 0; r2 < nruns; ++r2)
+        if (r2 != run) rank += run_lower_bound(base + (size_t)r2 * TK_RUN, key);
+    }
+    if (rank >= n_sorted) return;
+    // ---- decode + clip (bbox_transform.py:77-103, :125-133), every op individually rounded ----
+    const int i = (int)(unsigned)key;
     const int a = i % A, k = i / A;
     const int x = k % W, y = k / W;
     const float sx = (float)(x * feat_stride), sy = (float)(y * feat_stride);
-    const float ax1 = __fadd_rn(sh.anchors[a * 4 + 0], sx), ay1 = __fadd_rn(sh.anchors[a * 4 + 1], sy);
-    const float ax2 = __fadd_rn(sh.anchors[a * 4 + 2], sx), ay2 = __fadd_rn(sh.anchors[a * 4 + 3], sy);
+    const float ax1 = __fadd_rn(sh_anchors[a * 4 + 0], sx), ay1 = __fadd_rn(sh_anchors[a * 4 + 1], sy);
+    const float ax2 = __fadd_rn(sh_anchors[a * 4 + 2], sx), ay2 = __fadd_rn(sh_anchors[a * 4 + 3], sy);
     const float dx = __ldg(dl + (size_t)(a * 4 + 0) * K + k), dy = __ldg(dl + (size_t)(a * 4 + 1) * K + k);
     const float dw = __ldg(dl + (size_t)(a * 4 + 2) * K + k), dh = __ldg(dl + (size_t)(a * 4 + 3) * K + k);
     const float w = __fadd_rn(__fsub_rn(ax2, ax1), 1.0f), h = __fadd_rn(__fsub_rn(ay2, ay1), 1.0f);
@@ -457,8 +596,8 @@ __global__ void __launch_bounds__(TK_THREADS, 1)
     o.y = fminf(fmaxf(__fsub_rn(pcy, hh), 0.f), max_y);
     o.z = fminf(fmaxf(__fadd_rn(pcx, hw), 0.f), max_x);
     o.w = fminf(fmaxf(__fadd_rn(pcy, hh), 0.f), max_y);
-    reinterpret_cast<float4*>(boxes_out)[(size_t)img * n_sorted + r] = o;
-    if (order_out) order_out[(size_t)img * n_sorted + r] = i;
+    reinterpret_cast<float4*>(boxes_out)[(size_t)img * n_sorted + rank] = o;
+    if (order_out) order_out[(size_t)img * n_sorted + rank] = i;
   }
 }
 
@@ -466,34 +605,44 @@ __global__ void __launch_bounds__(TK_THREADS, 1)
 // host side
 // ===========================================================================
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-static inline int next_pow2(int v) {
-  int p = 1;
-  while (p < v) p <<= 1;
-  return p;
-}
 
 static int launch_mask_scan(const float* boxes, int batch, int n, int stride, float thresh,
                             int max_keep, unsigned long long* mask, int* keep, int keep_stride,
-                            int* num, float* rois_out, int post, cudaStream_t st) {
-  const int ncb = (n + 63) / 64;
-  if (ncb > 65535 || batch > 65535) return TLOD_ERR_UNSUPPORTED;
-  dim3 grid(ncb, ncb, batch);
+                            int* num, float* rois_out, int post, NmsState* state, cudaStream_t st) {
+  const int ncb = (n + 63) / 64, rs = nms_row_words(n);
+  if (batch > 65535) return TLOD_ERR_UNSUPPORTED;
   const bool filter = thresh >= 1e-6f && thresh <= 1e6f;
-  {
-    LaunchScope scope("nms_mask_kernel", st);
-    if (filter)
-      nms_mask_kernel<true><<<grid, 64, 0, st>>>(boxes, n, stride, thresh, mask);
-    else
-      nms_mask_kernel<false><<<grid, 64, 0, st>>>(boxes, n, stride, thresh, mask);
+  int prev = 0;
+  for (int phase = 1; prev < n; ++phase) {
+    const int end = nms_phase_end(n, max_keep, phase);
+    const int c0 = prev / 64, c1 = (end + 63) / 64;  // prev is a multiple of 64
+    const long long ntiles = (long long)c1 * (c1 + 1) / 2 - (long long)c0 * (c0 + 1) / 2;
+    long long per_img = ((long long)device_info().sm_count * 8 + batch - 1) / batch;  // 8 CTAs per SM
+    if (per_img > ntiles) per_img = ntiles;
+    if (per_img < 1) per_img = 1;
+    dim3 grid((unsigned)per_img, batch);
+    {
+      LaunchScope scope("nms_mask_kernel", st);
+      if (filter)
+        nms_mask_kernel<true><<<grid, 256, 0, st>>>(boxes, n, stride, thresh, mask, rs, c0, c1, phase == 1,
+                                                    state);
+      else
+        nms_mask_kernel<false><<<grid, 256, 0, st>>>(boxes, n, stride, thresh, mask, rs, c0, c1, phase == 1,
+                                                     state);
+    }
+    int rc = last_launch_status();
+    if (rc) return rc;
+    {
+      LaunchScope scope("nms_scan_kernel", st);
+      nms_scan_kernel<<<batch, SCAN_THREADS, (size_t)ncb * 8, st>>>(mask, n, max_keep, keep, keep_stride, num,
+                                                                  boxes, stride, rois_out, post, c0, c1,
+                                                                  end >= n, state, rs);
+    }
+    rc = last_launch_status();
+    if (rc) return rc;
+    prev = end;
   }
-  int rc = last_launch_status();
-  if (rc) return rc;
-  {
-    LaunchScope scope("nms_scan_kernel", st);
-    nms_scan_kernel<<<batch, SCAN_THREADS, (size_t)ncb * 8, st>>>(mask, n, max_keep, keep, keep_stride,
-                                                                num, boxes, stride, rois_out, post);
-  }
-  return last_launch_status();
+  return TLOD_OK;
 }
 
 }  // namespace tlod
@@ -502,8 +651,7 @@ using namespace tlod;
 
 extern "C" size_t tlod_nms_workspace_bytes(int n) {
   if (n <= 0) return 16;
-  const size_t ncb = (size_t)(n + 63) / 64;
-  return align_up((size_t)n * ncb * 8, 256) + 256;
+  return align_up((size_t)n * nms_row_words(n) * 8, 256) + 256;  // mask + NmsState
 }
 
 extern "C" int tlod_nms(const float* boxes, int n, int box_stride, float thresh, int max_keep,
@@ -520,8 +668,10 @@ extern "C" int tlod_nms(const float* boxes, int n, int box_stride, float thresh,
   if (!workspace || workspace_bytes < tlod_nms_workspace_bytes(n)) return TLOD_ERR_WORKSPACE;
   if (n > (1 << 20)) return TLOD_ERR_UNSUPPORTED;
   if (max_keep <= 0 || max_keep > n) max_keep = n;
+  if ((uintptr_t)workspace & 31) return TLOD_ERR_WORKSPACE;
+  NmsState* state = (NmsState*)((unsigned char*)workspace + align_up((size_t)n * nms_row_words(n) * 8, 256));
   return launch_mask_scan(boxes, 1, n, box_stride, thresh, max_keep,
-                          (unsigned long long*)workspace, keep_out, n, num_out, nullptr, 0, st);
+                          (unsigned long long*)workspace, keep_out, n, num_out, nullptr, 0, state, st);
 }
 
 extern "C" int tlod_proposals_n_sorted(int batch, int num_anchors, int height, int width,
@@ -534,19 +684,19 @@ extern "C" int tlod_proposals_n_sorted(int batch, int num_anchors, int height, i
 }
 
 struct ProposalWs {
-  size_t boxes, mask, keep, num, sortbuf, total;
+  size_t boxes, mask, keep, num, state, sortbuf, total;
 };
-static ProposalWs proposal_ws(int batch, int n_sorted, int post) {
+static ProposalWs proposal_ws(int batch, int n_sorted, int post, int nruns) {
   ProposalWs w;
-  const size_t ncb = (size_t)(n_sorted + 63) / 64;
-  const int n_pad = next_pow2(n_sorted);
+  const size_t ncb = (size_t)nms_row_words(n_sorted);
   size_t off = 0;
   w.boxes = off; off = align_up(off + (size_t)batch * n_sorted * 16, 256);
   w.mask = off;  off = align_up(off + (size_t)batch * n_sorted * ncb * 8, 256);
   w.keep = off;  off = align_up(off + (size_t)batch * (post > 0 ? post : n_sorted) * 4, 256);
   w.num = off;   off = align_up(off + (size_t)batch * 4, 256);
+  w.state = off; off = align_up(off + (size_t)batch * sizeof(NmsState), 256);
   w.sortbuf = off;
-  if (n_pad > TK_SMEM_SORT) off = align_up(off + (size_t)batch * n_pad * 8, 256);
+  off = align_up(off + (size_t)batch * nruns * TK_RUN * 8, 256);
   w.total = off + 256;
   return w;
 }
@@ -555,7 +705,8 @@ extern "C" size_t tlod_proposals_workspace_bytes(int batch, int num_anchors, int
                                                  int pre_nms_topN, int post_nms_topN) {
   if (batch <= 0 || num_anchors <= 0 || height <= 0 || width <= 0) return 0;
   const int n = tlod_proposals_n_sorted(batch, num_anchors, height, width, pre_nms_topN);
-  return proposal_ws(batch, n, post_nms_topN).total;
+  const int nruns = (num_anchors * height * width + TK_RUN - 1) / TK_RUN;
+  return proposal_ws(batch, n, post_nms_topN, nruns).total;
 }
 
 extern "C" int tlod_proposals(const float* scores, const float* deltas, const float* im_info,
@@ -571,8 +722,10 @@ extern "C" int tlod_proposals(const float* scores, const float* deltas, const fl
   const long long N = (long long)num_anchors * height * width;
   if (N >= (1 << 22)) return TLOD_ERR_UNSUPPORTED;
   const int n = tlod_proposals_n_sorted(batch, num_anchors, height, width, pre_nms_topN);
-  const ProposalWs w = proposal_ws(batch, n, post_nms_topN);
-  if (!workspace || workspace_bytes < w.total || ((uintptr_t)workspace & 15)) return TLOD_ERR_WORKSPACE;
+  const int nruns = (int)((N + TK_RUN - 1) / TK_RUN);
+  if (nruns > 32767 || batch > 65535) return TLOD_ERR_UNSUPPORTED;
+  const ProposalWs w = proposal_ws(batch, n, post_nms_topN, nruns);
+  if (!workspace || workspace_bytes < w.total || ((uintptr_t)workspace & 31)) return TLOD_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   unsigned char* base = (unsigned char*)workspace;
   float* boxes = sorted_boxes_out ? sorted_boxes_out : (float*)(base + w.boxes);
@@ -580,20 +733,20 @@ extern "C" int tlod_proposals(const float* scores, const float* deltas, const fl
   unsigned long long* mask = (unsigned long long*)(base + w.mask);
   int* keep = (int*)(base + w.keep);
   int* num = num_out ? num_out : (int*)(base + w.num);
-  const int n_pad = next_pow2(n);
-  size_t smem = sizeof(TKShared) + (n_pad <= TK_SMEM_SORT ? (size_t)n_pad * 8 : 0);
-  if (smem > (size_t)device_info().max_smem_optin) return TLOD_ERR_UNSUPPORTED;
-  cudaError_t e = cudaFuncSetAttribute(proposal_topk_decode_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
+  unsigned long long* runs = (unsigned long long*)(base + w.sortbuf);
   {
-    LaunchScope scope("proposal_topk_decode_kernel", st);
-    proposal_topk_decode_kernel<<<batch, TK_THREADS, smem, st>>>(
-        scores, deltas, im_info, anchors, num_anchors, height, width, feat_stride, n, n_pad,
-        (unsigned long long*)(base + w.sortbuf), boxes, order_out);
+    LaunchScope scope("proposal_sort_runs_kernel", st);
+    proposal_sort_runs_kernel<<<dim3(nruns, batch), TK_THREADS, 0, st>>>(scores, num_anchors, height * width, runs);
   }
   int rc = last_launch_status();
   if (rc) return rc;
+  {
+    LaunchScope scope("proposal_rank_decode_kernel", st);
+    proposal_rank_decode_kernel<<<dim3(2 * nruns, batch), TK_THREADS, 0, st>>>(
+        runs, deltas, im_info, anchors, num_anchors, height, width, feat_stride, n, boxes, order_out);
+  }
+  rc = last_launch_status();
+  if (rc) return rc;
   return launch_mask_scan(boxes, batch, n, 4, nms_thresh, post_nms_topN, mask, keep, post_nms_topN,
-                          num, rois_out, post_nms_topN, st);
+                          num, rois_out, post_nms_topN, (NmsState*)(base + w.state), st);
 }
