@@ -72,7 +72,12 @@ def synth_inputs(seed, pin=False):
 # this repo's arm
 # ---------------------------------------------------------------------------
 class TlodStep(object):
-    def __init__(self, dev, seed):
+    """One rank's step.  The device-only part (proposal layers, RoIAlignAvg forward + backward, DA
+    losses, GRL for both domains: ~45 launches, static shapes, no host synchronisation anywhere)
+    is captured once into a CUDA graph and replayed; the anchor-target layer follows eagerly
+    because its subsampling consumes numpy's host RNG exactly like the reference."""
+
+    def __init__(self, dev, seed, use_graph=True):
         from model.roi_align.modules.roi_align import RoIAlignAvg
         from model.rpn.anchor_target_layer import _AnchorTargetLayer
         from model.rpn.proposal_layer import _ProposalLayer
@@ -90,15 +95,18 @@ class TlodStep(object):
                     "tgt": torch.randn(N_TGT * ROIS_TGT, C, 7, 7, generator=g).to(dev)}
         self.num_boxes = torch.full((N_SRC,), 20, dtype=torch.long)
         np.random.seed(3)
+        self.graph = None
+        self.static = None
+        self.launches_per_replay = 0
+        self.host_out = None
+        if use_graph:
+            self.capture()
 
     def domain(self, dom, d, results):
         key = "TRAIN" if dom == "src" else "TEST"
         per = ROIS_SRC if dom == "src" else ROIS_TGT
         feat = d[dom + "_feat"].requires_grad_(True)
         rois = self.proposal((d[dom + "_prob"], d[dom + "_deltas"], d[dom + "_im_info"], key))
-        if dom == "src":
-            results["anchor_targets"] = self.anchor_target((d["src_prob"], d["src_gt"], d["src_im_info"],
-                                                            self.num_boxes))
         sel = rois[:, :per, :].reshape(-1, 5)  # stand-in for _ProposalTargetLayer's sampling
         pooled = self.roi_align(feat, sel)
         score = d[dom + "_img_score"].requires_grad_(True)
@@ -110,24 +118,72 @@ class TlodStep(object):
         g_feat = self.tlod.functional.grl_backward(feat.grad, 0.1)
         results[dom] = (rois, feat.grad, g_feat, torch.stack([img, ins, cst]).detach(), score.grad, prob.grad)
         feat.grad = None
+        score.grad = None
+        prob.grad = None
 
-    def step(self, d=None):
-        d = self.d if d is None else d
+    def device_part(self, d):
         results = {}
         self.domain("src", d, results)
         self.domain("tgt", d, results)
         return results
 
+    def anchor_part(self, d, results):
+        results["anchor_targets"] = self.anchor_target((d["src_prob"], d["src_gt"], d["src_im_info"],
+                                                        self.num_boxes))
+        return results
+
+    def capture(self):
+        """Warm up on a side stream, then capture device_part() over the static inputs self.d."""
+        try:
+            side = torch.cuda.Stream(self.dev)
+            side.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    self.device_part(self.d)
+            torch.cuda.current_stream(self.dev).wait_stream(side)
+            torch.cuda.synchronize(self.dev)
+            graph = torch.cuda.CUDAGraph()
+            n0 = self.tlod.launch_count()
+            with torch.cuda.graph(graph):
+                static = self.device_part(self.d)
+            self.launches_per_replay = int(self.tlod.launch_count() - n0)
+            graph.replay()
+            torch.cuda.synchronize(self.dev)
+            self.graph, self.static = graph, static
+        except Exception as e:  # noqa: BLE001 -- eager is always available
+            sys.stderr.write("bench.py: CUDA graph capture failed (%s); running eagerly\n" % (e,))
+            self.graph = self.static = None
+
+    def step(self, d=None):
+        d = self.d if d is None else d
+        # anchor targets: launch the label kernel first (own stream), queue the rest of the step,
+        # then do the host-side subsampling while the GPU works through the queue
+        pending = self.anchor_target.begin((d["src_prob"], d["src_gt"], d["src_im_info"], self.num_boxes))
+        if self.graph is not None and d is self.d:
+            self.graph.replay()
+            results = dict(self.static)
+        else:
+            results = self.device_part(d)
+        results["anchor_targets"] = self.anchor_target.finish(pending)
+        return results
+
     def step_e2e(self):
-        """Same step through host buffers: H2D of the inputs from pinned memory, D2H of the results."""
-        d = {k: v.to(self.dev, non_blocking=True) for k, v in self.host.items()}
-        r = self.step(d)
-        out = []
+        """Same step through host buffers: H2D of the inputs from pinned memory into the static
+        device buffers, the step, D2H of the results into pinned host buffers."""
+        for k, v in self.host.items():
+            self.d[k].detach().copy_(v, non_blocking=True)
+        r = self.step()
+        outs = []
         for dom in ("src", "tgt"):
             rois, gfeat, _, losses, _, _ = r[dom]
-            out += [rois.cpu(), gfeat.cpu(), losses.cpu()]
-        out.append(r["anchor_targets"][0].cpu())
-        return out
+            outs += [rois, gfeat, losses]
+        outs.append(r["anchor_targets"][0])
+        if self.host_out is None:
+            self.host_out = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
+        for h, o in zip(self.host_out, outs):
+            h.copy_(o, non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        return self.host_out
 
     def e2e_bytes(self):
         h2d = sum(v.numel() * v.element_size() for v in self.host.values())
@@ -220,7 +276,7 @@ def run_tlod(args):
     import tlod_b200
     from tlod_b200 import _lib
 
-    step = TlodStep(dev, seed=3 + rank)
+    step = TlodStep(dev, seed=3 + rank, use_graph=not args.no_graph)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
 
     def barrier():
@@ -255,7 +311,10 @@ def run_tlod(args):
     sampler = clocks_sampler(clock_file) if rank == 0 else None
     launches0 = tlod_b200.launch_count()
     ms_dev, wall = timed(step.step, args.steps, args.warmup)
-    launches = (tlod_b200.launch_count() - launches0) // (args.steps + args.warmup) * args.steps
+    # kernels of this library inside the timed region: eager launches are counted by the library;
+    # a graph replay re-issues the launches counted once at capture time
+    eager_per_step = (tlod_b200.launch_count() - launches0) // (args.steps + args.warmup)
+    launches = (eager_per_step + (step.launches_per_replay if step.graph is not None else 0)) * args.steps
     ms_e2e, _ = timed(step.step_e2e, args.steps, max(3, args.warmup // 2))
     if sampler is not None:
         sampler.terminate()
@@ -266,7 +325,7 @@ def run_tlod(args):
     _lib.profile(True)
     for _ in range(max(5, min(args.steps, 20))):
         flush.zero_()
-        step.step()
+        step.anchor_part(step.d, step.device_part(step.d))  # eager: the library brackets each launch
     torch.cuda.synchronize()
     prof = _lib.profile_read()
     _lib.profile(False)
@@ -324,6 +383,7 @@ def run_tlod(args):
         "e2e": {"value": world * ROIS_PER_STEP * args.steps / (ms_e2e * 1e-3), "unit": "RoIs/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
+        "cuda_graph": step.graph is not None,
         "clocks": parse_clocks(clock_file),
         "roofline": roofline, "roofline_roi_align_bwd": roofline_bwd,
         "dominant_kernel": dominant, "kernels": kernels, "roi_align_cfg3": cfg3,
@@ -417,6 +477,7 @@ def main():
     ap.add_argument("--impl", default="tlod", choices=["tlod", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cfg3", action="store_true", help="skip the cfg3-scale RoIAlign roofline section")
+    ap.add_argument("--no-graph", action="store_true", help="run the device part eagerly instead of a CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -6,7 +6,8 @@ Same constructor and forward((rpn_cls_score, gt_boxes, im_info, num_boxes)) -> l
 Device work is two fused passes (tlod_anchor_labels: IoU + per-gt max + label rules, no
 (B,N,K) tensor; tlod_anchor_targets_finalize: targets + weights + unmap + permute).  The
 random subsampling stays on the host with numpy's global RNG, consumed in exactly the
-reference's order (:123-145), because the RNG stream position is data dependent."""
+reference's order (:123-145), because the RNG stream position is data dependent: the (B, n)
+label array makes one pinned round trip (the reference synchronises 2 + 2B times)."""
 import numpy as np
 import torch
 import torch.nn as nn
@@ -27,6 +28,8 @@ class _AnchorTargetLayer(nn.Module):
         self._num_anchors = self._anchors.size(0)
         self._allowed_border = 0
         self._cache = {}
+        self._stream = None
+        self._labels_host = None
 
     def _inside(self, feat_h, feat_w, lim_w, lim_h, device):
         """Inside-image anchors for this map size (:66-91): (anchors (n,4), inds (n,), inverse (total,))."""
@@ -52,43 +55,63 @@ class _AnchorTargetLayer(nn.Module):
         return hit
 
     def forward(self, input):
+        return self.finish(self.begin(input))
+
+    # forward() = finish(begin()).  The two halves exist so that a caller can enqueue other GPU
+    # work between them: begin() only launches (label kernel + a pinned D2H copy on this layer's
+    # own stream), finish() waits for that copy alone -- not for whatever else the caller has
+    # queued meanwhile -- runs the host-side subsampling and launches the finalize kernel.
+    def begin(self, input):
         rpn_cls_score, gt_boxes, im_info, num_boxes = input[0], input[1], input[2], input[3]
         height, width = rpn_cls_score.size(2), rpn_cls_score.size(3)
+        dev = gt_boxes.device
+        if self._stream is None or self._stream.device != dev:
+            self._stream = torch.cuda.Stream(dev)
+        cur = torch.cuda.current_stream(dev)
+        self._stream.wait_stream(cur)  # inputs produced on the caller's stream
+        with torch.cuda.stream(self._stream):
+            # :86-87 -- the FIRST image's size, truncated to int, is used for the whole batch
+            info0 = im_info[0].tolist()
+            anchors, inds_inside, inv_index = self._inside(height, width, int(info0[1]), int(info0[0]), dev)
+            labels, argmax = F.anchor_labels(anchors, gt_boxes, cfg.TRAIN.RPN_NEGATIVE_OVERLAP,
+                                             cfg.TRAIN.RPN_POSITIVE_OVERLAP, cfg.TRAIN.RPN_CLOBBER_POSITIVES)
+            if self._labels_host is None or self._labels_host.shape != labels.shape:
+                self._labels_host = torch.empty(labels.shape, dtype=labels.dtype).pin_memory()
+            self._labels_host.copy_(labels, non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record(self._stream)
+        for t in (gt_boxes, im_info):
+            t.record_stream(self._stream)
+        return (labels, argmax, anchors, inv_index, gt_boxes, height, width, copied, cur)
+
+    def finish(self, state):
+        labels, argmax, anchors, inv_index, gt_boxes, height, width, copied, cur = state
         batch_size = gt_boxes.size(0)
         A = self._num_anchors
-        # :86-87 -- the FIRST image's size, truncated to int, is used for the whole batch
-        info0 = im_info[0].tolist()
-        anchors, inds_inside, inv_index = self._inside(height, width, int(info0[1]), int(info0[0]),
-                                                       gt_boxes.device)
+        copied.synchronize()
+        lab = self._labels_host.numpy()  # (B, n) fp32 in {-1, 0, 1}: edited in place on the host
 
-        labels, argmax = F.anchor_labels(anchors, gt_boxes, cfg.TRAIN.RPN_NEGATIVE_OVERLAP,
-                                         cfg.TRAIN.RPN_POSITIVE_OVERLAP, cfg.TRAIN.RPN_CLOBBER_POSITIVES)
-
-        # ---- host-side subsampling, :118-145 (same tensor ops, same RNG calls) ----
+        # ---- host-side subsampling, :118-145: same index order, same RNG calls ----
         num_fg = int(cfg.TRAIN.RPN_FG_FRACTION * cfg.TRAIN.RPN_BATCHSIZE)
-        counts = torch.stack([torch.sum((labels == 1).int(), 1), torch.sum((labels == 0).int(), 1)]).tolist()
-        sum_fg, sum_bg = counts[0], counts[1]
         i = 0
         for i in range(batch_size):
-            if sum_fg[i] > num_fg:
-                fg_inds = torch.nonzero(labels[i] == 1).view(-1)
-                rand_num = torch.from_numpy(np.random.permutation(fg_inds.size(0))).to(fg_inds.device).long()
-                disable_inds = fg_inds[rand_num[:fg_inds.size(0) - num_fg]]
-                labels[i][disable_inds] = -1
+            fg_inds = np.nonzero(lab[i] == 1)[0]
+            if fg_inds.shape[0] > num_fg:
+                rand_num = np.random.permutation(fg_inds.shape[0])
+                lab[i][fg_inds[rand_num[:fg_inds.shape[0] - num_fg]]] = -1
                 n_fg_i = num_fg
             else:
-                n_fg_i = sum_fg[i]
+                n_fg_i = fg_inds.shape[0]
             num_bg = cfg.TRAIN.RPN_BATCHSIZE - n_fg_i
-            if sum_bg[i] > num_bg:
-                bg_inds = torch.nonzero(labels[i] == 0).view(-1)
-                rand_num = torch.from_numpy(np.random.permutation(bg_inds.size(0))).to(bg_inds.device).long()
-                disable_inds = bg_inds[rand_num[:bg_inds.size(0) - num_bg]]
-                labels[i][disable_inds] = -1
+            bg_inds = np.nonzero(lab[i] == 0)[0]
+            if bg_inds.shape[0] > num_bg:
+                rand_num = np.random.permutation(bg_inds.shape[0])
+                lab[i][bg_inds[rand_num[:bg_inds.shape[0] - num_bg]]] = -1
 
         inside_w = cfg.TRAIN.RPN_BBOX_INSIDE_WEIGHTS[0]
         if cfg.TRAIN.RPN_POSITIVE_WEIGHT < 0:
             # :155-158 -- num_examples of the LAST image (stale loop variable) for every image
-            num_examples = int(torch.sum(labels[i] >= 0).item())
+            num_examples = int((lab[i] >= 0).sum())
             positive_weights = 1.0 / num_examples if num_examples > 0 else float('inf')
             negative_weights = positive_weights
         else:
@@ -96,10 +119,14 @@ class _AnchorTargetLayer(nn.Module):
             raise NotImplementedError("RPN_POSITIVE_WEIGHT >= 0 leaves the weights undefined in the "
                                       "reference as well (anchor_target_layer.py:159-164)")
 
-        labels_out, targets, inside, outside = F.anchor_targets_finalize(
-            labels, argmax, anchors, gt_boxes, inv_index, A, height, width, inside_w, positive_weights,
-            negative_weights)
-        return [labels_out, targets, inside, outside]
+        with torch.cuda.stream(self._stream):
+            labels.copy_(self._labels_host, non_blocking=True)
+            out = F.anchor_targets_finalize(labels, argmax, anchors, gt_boxes, inv_index, A, height, width,
+                                            inside_w, positive_weights, negative_weights)
+        torch.cuda.current_stream(gt_boxes.device).wait_stream(self._stream)
+        for t in out:
+            t.record_stream(torch.cuda.current_stream(gt_boxes.device))
+        return list(out)
 
     def backward(self, top, propagate_down, bottom):
         """This layer does not propagate gradients."""
