@@ -102,6 +102,17 @@ int tlod_roi_align_backward(const float* top_grad, const float* rois, float* bot
                             int aligned_h, int aligned_w, float spatial_scale, const void* plan,
                             size_t plan_bytes, void* stream);
 
+/* 2x2 / stride-1 average pooling of every (height, width) tile -> (height-1, width-1):
+ * the `avg_pool2d(x, kernel_size=2, stride=1)` of RoIAlignAvg
+ * (lib/model/roi_align/modules/roi_align.py:26-29).  in (tiles, height, width),
+ * out (tiles, height-1, width-1); tiles = num_rois * channels.  The backward entry is the
+ * adjoint: grad_out (tiles, height-1, width-1) -> grad_in (tiles, height, width), fully
+ * overwritten. */
+int tlod_avgpool2x2_forward(const float* in, float* out, long long tiles, int height, int width,
+                            void* stream);
+int tlod_avgpool2x2_backward(const float* grad_out, float* grad_in, long long tiles, int height,
+                             int width, void* stream);
+
 /* ------------------------------------------------------------------------ */
 /* RoIPool                                                                    */
 /* replaces roi_pooling_forward_cuda / roi_pooling_backward_cuda              */

@@ -108,6 +108,24 @@ def test_roi_align_small_and_huge_rois_column_chain():
     assert np.array_equal(grad, grad2)
 
 
+@pytest.mark.parametrize("shape", [(37, 16, 8, 8), (1, 1, 8, 8), (1030, 3, 8, 8), (5, 7, 15, 15), (9, 4, 3, 6)])
+def test_avgpool2x2_matches_torch(shape):
+    """tlod_avgpool2x2_forward/backward == avg_pool2d(kernel_size=2, stride=1) and its adjoint."""
+    from tlod_b200 import functional as F
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=g)
+    xd = x.to(DEV)
+    y = F.avgpool2x2_forward(xd)
+    ref = torch.nn.functional.avg_pool2d(x, kernel_size=2, stride=1)
+    assert y.shape == ref.shape
+    assert rel_err(y.cpu().numpy(), ref.numpy()) <= 1e-6
+    top = torch.randn(*ref.shape, generator=g)
+    xr = x.clone().requires_grad_(True)
+    torch.nn.functional.avg_pool2d(xr, kernel_size=2, stride=1).backward(top)
+    gx = F.avgpool2x2_backward(top.to(DEV))
+    assert rel_err(gx.cpu().numpy(), xr.grad.numpy()) <= 1e-6
+
+
 def test_roi_align_invalid_batch_index_gives_zeros():
     from tlod_b200 import functional as F
     feat, rois, AH, AW, scale = _case("multi_image_res_conv4")

@@ -5,6 +5,8 @@ with features (B,C,H,W) fp32 CUDA and rois (R,5) = [batch_idx, x1, y1, x2, y2]."
 from torch.nn.functional import avg_pool2d, max_pool2d
 from torch.nn.modules.module import Module
 
+from tlod_b200.autograd import RoIAlignAvgFunction
+
 from ..functions.roi_align import RoIAlignFunction
 
 
@@ -27,8 +29,10 @@ class RoIAlignAvg(Module):
         self.spatial_scale = float(spatial_scale)
 
     def forward(self, features, rois):
-        x = RoIAlignFunction(self.aligned_height + 1, self.aligned_width + 1, self.spatial_scale)(features, rois)
-        return avg_pool2d(x, kernel_size=2, stride=1)
+        # RoIAlign at (h+1, w+1), then avg_pool2d(kernel_size=2, stride=1): both halves in this
+        # library's kernels, one autograd node (the (h+1, w+1) intermediate is not kept)
+        return RoIAlignAvgFunction.apply(features, rois, self.aligned_height, self.aligned_width,
+                                         self.spatial_scale)
 
 
 class RoIAlignMax(Module):

@@ -30,6 +30,8 @@ SIGNATURES = {
                                        c_size_t, P]),
     "tlod_roi_align_backward": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P,
                                         c_size_t, P]),
+    "tlod_avgpool2x2_forward": (c_int, [P, P, c_longlong, c_int, c_int, P]),
+    "tlod_avgpool2x2_backward": (c_int, [P, P, c_longlong, c_int, c_int, P]),
     "tlod_roi_pool_forward": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P]),
     "tlod_roi_pool_backward": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P]),
     "tlod_nms_workspace_bytes": (c_size_t, [c_int]),

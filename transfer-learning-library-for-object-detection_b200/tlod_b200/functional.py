@@ -105,6 +105,32 @@ def roi_align_backward(top_grad, rois, feature_size, spatial_scale: float, plan=
     return grad
 
 
+def avgpool2x2_forward(x):
+    """(..., h, w) -> (..., h-1, w-1): avg_pool2d(kernel_size=2, stride=1)."""
+    _require_cuda(x)
+    x = _f32(x)
+    h, w = int(x.shape[-2]), int(x.shape[-1])
+    out = torch.empty(tuple(x.shape[:-2]) + (h - 1, w - 1), dtype=torch.float32, device=x.device)
+    tiles = x.numel() // (h * w)
+    with torch.cuda.device(x.device):
+        check(lib.tlod_avgpool2x2_forward(x.data_ptr(), out.data_ptr(), tiles, h, w, _stream(x.device)),
+              "tlod_avgpool2x2_forward")
+    return out
+
+
+def avgpool2x2_backward(grad_out):
+    """Adjoint of avgpool2x2_forward: (..., h-1, w-1) -> (..., h, w)."""
+    _require_cuda(grad_out)
+    g = _f32(grad_out)
+    h, w = int(g.shape[-2]) + 1, int(g.shape[-1]) + 1
+    out = torch.empty(tuple(g.shape[:-2]) + (h, w), dtype=torch.float32, device=g.device)
+    tiles = out.numel() // (h * w)
+    with torch.cuda.device(g.device):
+        check(lib.tlod_avgpool2x2_backward(g.data_ptr(), out.data_ptr(), tiles, h, w, _stream(g.device)),
+              "tlod_avgpool2x2_backward")
+    return out
+
+
 def roi_pool_forward(features, rois, pooled_h: int, pooled_w: int, spatial_scale: float):
     _require_cuda(features, rois)
     features, rois = _f32(features), _f32(rois)
