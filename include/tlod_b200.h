@@ -135,6 +135,25 @@ int tlod_roi_pool_backward(const float* top_grad, const int* argmax, const float
                            void* stream);
 
 /* ------------------------------------------------------------------------ */
+/* RoICrop (bilinear sampler on a per-RoI grid; BASELINE cfg3 "crop 14")      */
+/* replaces BilinearSamplerBHWD_updateOutput_cuda / _updateGradInput_cuda     */
+/*   lib/model/roi_crop/src/roi_crop_cuda.c, roi_crop_cuda.h:5-8              */
+/*   (kernels lib/model/roi_crop/src/roi_crop_cuda_kernel.cu:45-108, :111-190)*/
+/* ------------------------------------------------------------------------ */
+/* features (in_batch, channels, height, width); grid_yx (out_batch, grid_h, grid_w, 2) =
+ * (y, x) in [-1, 1] (align_corners semantics: -1 / +1 are the centres of the first / last
+ * cell); output (out_batch, channels, grid_h, grid_w).  Output batch b samples image
+ * b / (out_batch / in_batch); corners outside the map contribute zero.
+ * The backward entry overwrites grad_features with the gradient w.r.t. the features; like
+ * the reference kernel it produces no gradient for the grid. */
+int tlod_roi_crop_forward(const float* features, const float* grid_yx, float* output, int in_batch,
+                          int channels, int height, int width, int out_batch, int grid_h, int grid_w,
+                          void* stream);
+int tlod_roi_crop_backward(const float* grad_output, const float* grid_yx, float* grad_features,
+                           int in_batch, int channels, int height, int width, int out_batch,
+                           int grid_h, int grid_w, void* stream);
+
+/* ------------------------------------------------------------------------ */
 /* NMS                                                                        */
 /* replaces nms_cuda                lib/model/nms/src/nms_cuda.c:8-19         */
 /*   (nms_kernel + host greedy scan lib/model/nms/src/nms_cuda_kernel.cu:41-161)*/

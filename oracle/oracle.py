@@ -122,6 +122,47 @@ def roi_pool_backward(top_grad, argmax, rois, feature_shape, spatial_scale):
 
 
 # ---------------------------------------------------------------------------
+# RoICrop   (lib/model/roi_crop/src/roi_crop_cuda_kernel.cu:12-23, 45-108, 111-190)
+# ---------------------------------------------------------------------------
+def roi_crop_forward(features, grid_yx):
+    """features (ib, C, H, W), grid_yx (ob, GH, GW, 2) in [-1, 1] -> (ob, C, GH, GW)."""
+    feat, fp = _f(features)
+    g, gp = _f(grid_yx)
+    ib, C, H, W = feat.shape
+    ob, GH, GW, _ = g.shape
+    out = np.empty((ob, C, GH, GW), np.float32)
+    lib().orc_roi_crop_fwd(fp, gp, out.ctypes.data_as(c_float_p), ib, C, H, W, ob, GH, GW)
+    return out
+
+
+def roi_crop_backward(grad_out, grid_yx, feature_shape):
+    """-> gradient w.r.t. the features (the reference kernel produces none for the grid)."""
+    go, gop = _f(grad_out)
+    g, gp = _f(grid_yx)
+    ib, C, H, W = feature_shape
+    ob, GH, GW, _ = g.shape
+    out = np.empty((ib, C, H, W), np.float32)
+    lib().orc_roi_crop_bwd(gop, gp, out.ctypes.data_as(c_float_p), ib, C, H, W, ob, GH, GW)
+    return out
+
+
+def affine_grid_gen(rois, input_size, grid_size):
+    """_affine_grid_gen (lib/model/utils/net_utils.py:142-164) with torch-0.4's affine_grid
+    (= align_corners=True): returns grid_xy (R, G, G, 2)."""
+    rois = np.asarray(rois, np.float32)
+    x1, y1, x2, y2 = [rois[:, k] / np.float32(16.0) for k in (1, 2, 3, 4)]
+    height, width = np.float32(input_size[0]), np.float32(input_size[1])
+    t00 = (x2 - x1) / (width - 1)
+    t02 = (x1 + x2 - width + 1) / (width - 1)
+    t11 = (y2 - y1) / (height - 1)
+    t12 = (y1 + y2 - height + 1) / (height - 1)
+    lin = np.linspace(-1.0, 1.0, grid_size, dtype=np.float32) if grid_size > 1 else np.zeros(1, np.float32)
+    gx = t00[:, None, None] * lin[None, None, :] + t02[:, None, None] + 0 * lin[None, :, None]
+    gy = t11[:, None, None] * lin[None, :, None] + t12[:, None, None] + 0 * lin[None, None, :]
+    return np.stack([gx, gy], axis=3).astype(np.float32)
+
+
+# ---------------------------------------------------------------------------
 # NMS   (lib/model/nms/src/nms_cuda_kernel.cu:31-39, 41-85, 132-144)
 # ---------------------------------------------------------------------------
 def nms(dets, thresh, max_keep=0):

@@ -467,6 +467,89 @@ void orc_anchor_labels(const float* overlaps, int B, int N, int K, float neg_thr
   }
 }
 
+/* ------------------------------------------------------------------ */
+/* RoICrop = bilinear sampler over a (y, x) grid in [-1, 1]            */
+/* lib/model/roi_crop/src/roi_crop_cuda_kernel.cu:12-23 (getTopLeft),  */
+/* :45-108 (forward), :111-190 (backward: gradient w.r.t. the images   */
+/* only -- the kernel never writes gradGrids).                         */
+/* input (ib, C, H, W) NCHW, grid (ob, GH, GW, 2) = (y, x), output     */
+/* (ob, C, GH, GW); output batch b samples image b / (ob / ib).        */
+/* ------------------------------------------------------------------ */
+static void orc_top_left(float x, int size, int* point, float* weight) {
+  float coord = (x + 1.0f) * (float)(size - 1) / 2.0f;
+  float fl = floorf(coord);
+  *point = (int)fl;
+  *weight = 1.0f - (coord - fl);
+}
+
+void orc_roi_crop_fwd(const float* input, const float* grid, float* output, int ib, int C, int H,
+                      int W, int ob, int GH, int GW) {
+  const int per = ob / ib;
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < ob; ++b) {
+    const int bi = b / per;
+    for (int y = 0; y < GH; ++y)
+      for (int x = 0; x < GW; ++x) {
+        const float yf = grid[(((size_t)b * GH + y) * GW + x) * 2 + 0];
+        const float xf = grid[(((size_t)b * GH + y) * GW + x) * 2 + 1];
+        int xi, yi;
+        float xw, yw;
+        orc_top_left(xf, W, &xi, &xw);
+        orc_top_left(yf, H, &yi, &yw);
+        const int tl = xi >= 0 && xi <= W - 1 && yi >= 0 && yi <= H - 1;
+        const int tr = xi + 1 >= 0 && xi + 1 <= W - 1 && yi >= 0 && yi <= H - 1;
+        const int bl = xi >= 0 && xi <= W - 1 && yi + 1 >= 0 && yi + 1 <= H - 1;
+        const int br = xi + 1 >= 0 && xi + 1 <= W - 1 && yi + 1 >= 0 && yi + 1 <= H - 1;
+        for (int c = 0; c < C; ++c) {
+          const float* p = input + ((size_t)bi * C + c) * H * W;
+          float v = 0.f;
+          if (tl || tr || bl || br) {
+            const float a = tl ? p[yi * W + xi] : 0.f;
+            const float bb = tr ? p[yi * W + xi + 1] : 0.f;
+            const float cc = bl ? p[(yi + 1) * W + xi] : 0.f;
+            const float d = br ? p[(yi + 1) * W + xi + 1] : 0.f;
+            v = xw * yw * a + (1 - xw) * yw * bb + xw * (1 - yw) * cc + (1 - xw) * (1 - yw) * d;
+          }
+          output[(((size_t)b * C + c) * GH + y) * GW + x] = v;
+        }
+      }
+  }
+}
+
+/* grad_input (ib, C, H, W) accumulated in double, then rounded */
+void orc_roi_crop_bwd(const float* grad_out, const float* grid, float* grad_input, int ib, int C,
+                      int H, int W, int ob, int GH, int GW) {
+  const int per = ob / ib;
+  const size_t total = (size_t)ib * C * H * W;
+  double* acc = (double*)calloc(total, sizeof(double));
+  for (int b = 0; b < ob; ++b) {
+    const int bi = b / per;
+    for (int y = 0; y < GH; ++y)
+      for (int x = 0; x < GW; ++x) {
+        const float yf = grid[(((size_t)b * GH + y) * GW + x) * 2 + 0];
+        const float xf = grid[(((size_t)b * GH + y) * GW + x) * 2 + 1];
+        int xi, yi;
+        float xw, yw;
+        orc_top_left(xf, W, &xi, &xw);
+        orc_top_left(yf, H, &yi, &yw);
+        const int tl = xi >= 0 && xi <= W - 1 && yi >= 0 && yi <= H - 1;
+        const int tr = xi + 1 >= 0 && xi + 1 <= W - 1 && yi >= 0 && yi <= H - 1;
+        const int bl = xi >= 0 && xi <= W - 1 && yi + 1 >= 0 && yi + 1 <= H - 1;
+        const int br = xi + 1 >= 0 && xi + 1 <= W - 1 && yi + 1 >= 0 && yi + 1 <= H - 1;
+        for (int c = 0; c < C; ++c) {
+          const float g = grad_out[(((size_t)b * C + c) * GH + y) * GW + x];
+          double* p = acc + ((size_t)bi * C + c) * H * W;
+          if (tl) p[yi * W + xi] += (double)(xw * yw * g);
+          if (tr) p[yi * W + xi + 1] += (double)((1 - xw) * yw * g);
+          if (bl) p[(yi + 1) * W + xi] += (double)(xw * (1 - yw) * g);
+          if (br) p[(yi + 1) * W + xi + 1] += (double)((1 - xw) * (1 - yw) * g);
+        }
+      }
+  }
+  for (size_t i = 0; i < total; ++i) grad_input[i] = (float)acc[i];
+  free(acc);
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

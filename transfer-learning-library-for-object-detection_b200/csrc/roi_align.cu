@@ -977,6 +977,15 @@ extern "C" int tlod_roi_align_backward(const float* top_grad, const float* rois,
       band_rows = (int)((budget / (BW_CH * sizeof(float)) - 1) / width);
     }
     if (band_rows > height) band_rows = height;
+    // small problems: thinner bands (more CTAs) until the grid covers two CTAs per SM -- a CTA's
+    // item loop is serial, so an under-filled machine costs more than the re-read of the
+    // gradient rows that straddle two bands
+    {
+      const long long per_band = (long long)batch * ((channels + BW_CH - 1) / BW_CH);
+      while (band_rows > 1 &&
+             per_band * ((height + band_rows - 1) / band_rows) < 2LL * device_info().sm_count)
+        band_rows = (band_rows + 1) / 2;
+    }
     CUtensorMap tmap;
     if (band_rows >= 1 && make_grad_tmap(&tmap, top_grad, num_rois, channels, aligned_h)) {
       const int Sb = (band_rows * width) | 1;  // odd stride: lane = channel is conflict free

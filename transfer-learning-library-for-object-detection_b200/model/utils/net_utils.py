@@ -1,0 +1,34 @@
+"""The pieces of lib/model/utils/net_utils.py on the RoI path.
+
+``_affine_grid_gen`` (net_utils.py:142-164): theta from the RoIs (image px / 16) and
+``F.affine_grid``.  The reference ran on torch 0.4, whose affine_grid is what torch >= 1.3
+calls ``align_corners=True``; that is passed explicitly here (the default changed)."""
+import torch
+import torch.nn.functional as F
+
+
+def _affine_grid_gen(rois, input_size, grid_size):
+    rois = rois.detach()
+    x1 = rois[:, 1::4] / 16.0
+    y1 = rois[:, 2::4] / 16.0
+    x2 = rois[:, 3::4] / 16.0
+    y2 = rois[:, 4::4] / 16.0
+    height = input_size[0]
+    width = input_size[1]
+    zero = rois.new_zeros((rois.size(0), 1))
+    theta = torch.cat([
+        (x2 - x1) / (width - 1),
+        zero,
+        (x1 + x2 - width + 1) / (width - 1),
+        zero,
+        (y2 - y1) / (height - 1),
+        (y1 + y2 - height + 1) / (height - 1)], 1).view(-1, 2, 3)
+    return F.affine_grid(theta, torch.Size((rois.size(0), 1, grid_size, grid_size)), align_corners=True)
+
+
+def roi_crop_pool(roi_crop, base_feat, rois, grid_size):
+    """The cfg.POOLING_MODE == 'crop' branch of lib/model/faster_rcnn/faster_rcnn.py:77-83:
+    affine grid -> (y, x) order -> RoICrop -> (optional) 2x2 max pool is left to the caller."""
+    grid_xy = _affine_grid_gen(rois.view(-1, 5), base_feat.size()[2:], grid_size)
+    grid_yx = torch.stack([grid_xy[:, :, :, 1], grid_xy[:, :, :, 0]], 3).contiguous()
+    return roi_crop(base_feat, grid_yx.detach())

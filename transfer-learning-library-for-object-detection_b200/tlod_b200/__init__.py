@@ -9,9 +9,9 @@ reference's ``_init_paths.py`` adds ``lib/``.
 from . import _lib  # noqa: F401  (raises if libtlod_b200.so is missing)
 from . import functional  # noqa: F401
 from .autograd import (DALossFunction, GradReverse, RoIAlignAvgFunction, RoIAlignFunction,  # noqa: F401
-                       RoIPoolFunction, da_losses,
+                       RoICropFunction, RoIPoolFunction, da_losses,
                        grad_reverse)
 from ._lib import TlodError, launch_count  # noqa: F401
 
-__all__ = ["functional", "RoIAlignFunction", "RoIAlignAvgFunction", "RoIPoolFunction", "GradReverse", "grad_reverse", "DALossFunction",
+__all__ = ["functional", "RoIAlignFunction", "RoIAlignAvgFunction", "RoICropFunction", "RoIPoolFunction", "GradReverse", "grad_reverse", "DALossFunction",
            "da_losses", "TlodError", "launch_count"]

@@ -78,6 +78,22 @@ class RoIPoolFunction(Function):
         return grad_input, None, None, None, None
 
 
+class RoICropFunction(Function):
+    """(features (ib,C,H,W), grid_yx (ob,GH,GW,2)) -> (ob,C,GH,GW); lib/model/roi_crop/functions/
+    roi_crop.py:7-21.  Like the reference kernel, the gradient of the grid is all zeros."""
+
+    @staticmethod
+    def forward(ctx, input1, input2):
+        ctx.save_for_backward(input2)
+        ctx.feature_size = tuple(input1.shape)
+        return F.roi_crop_forward(input1, input2)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        (grid,) = ctx.saved_tensors
+        return F.roi_crop_backward(grad_output, grid, ctx.feature_size), torch.zeros_like(grid)
+
+
 class GradReverse(Function):
     """Identity forward; backward -alpha * g (optionally * per-row weight, lib/MAF/DA.py:34-53)."""
 

@@ -161,6 +161,33 @@ def roi_pool_backward(top_grad, argmax, rois, feature_size, spatial_scale: float
     return grad
 
 
+def roi_crop_forward(features, grid_yx):
+    """features (ib, C, H, W), grid_yx (ob, GH, GW, 2) -> (ob, C, GH, GW)."""
+    _require_cuda(features, grid_yx)
+    features, grid_yx = _f32(features), _f32(grid_yx)
+    ib, C, H, W = features.shape
+    ob, GH, GW, two = grid_yx.shape
+    if two != 2:
+        raise ValueError("grid must be (N, GH, GW, 2) = (y, x)")
+    out = torch.empty((ob, C, GH, GW), dtype=torch.float32, device=features.device)
+    with torch.cuda.device(features.device):
+        check(lib.tlod_roi_crop_forward(features.data_ptr(), grid_yx.data_ptr(), out.data_ptr(), ib, C, H, W, ob,
+                                        GH, GW, _stream(features.device)), "tlod_roi_crop_forward")
+    return out
+
+
+def roi_crop_backward(grad_output, grid_yx, feature_size):
+    _require_cuda(grad_output, grid_yx)
+    grad_output, grid_yx = _f32(grad_output), _f32(grid_yx)
+    ib, C, H, W = [int(v) for v in feature_size]
+    ob, GH, GW, _ = grid_yx.shape
+    grad = torch.empty((ib, C, H, W), dtype=torch.float32, device=grad_output.device)
+    with torch.cuda.device(grad_output.device):
+        check(lib.tlod_roi_crop_backward(grad_output.data_ptr(), grid_yx.data_ptr(), grad.data_ptr(), ib, C, H, W,
+                                         ob, GH, GW, _stream(grad_output.device)), "tlod_roi_crop_backward")
+    return grad
+
+
 # ---------------------------------------------------------------------------
 # NMS / proposals
 # ---------------------------------------------------------------------------
