@@ -8,6 +8,7 @@ reference's ``_init_paths.py`` adds ``lib/``.
 """
 from . import _lib  # noqa: F401  (raises if libtlod_b200.so is missing)
 from . import functional  # noqa: F401
+from . import sharding  # noqa: F401
 from .autograd import (DALossFunction, GradReverse, RoIAlignAvgFunction, RoIAlignFunction,  # noqa: F401
                        RoICropFunction, RoIPoolFunction, da_losses,
                        grad_reverse)
