@@ -442,7 +442,7 @@ def run_tlod(args):
     }
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference(steps=2, warmup=0, threads=os.cpu_count())
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -517,10 +517,25 @@ def run_reference(args):
         "note": "the reference's CUDA path cannot load on torch 2.x (torch.utils.ffi) and its CPU RoIAlign "
                 "backward / nms_cpu are wrong (SURVEY.md 8c), so the CPU arm is the oracle port of its kernels",
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_JSON_OUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else any library prints on fd 1
+    (e.g. NCCL's version banner) has been diverted to stderr by main()."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
