@@ -244,6 +244,32 @@ int tlod_anchor_targets_finalize(const float* labels, const int* argmax, const f
                                  float positive_weight, float negative_weight, void* stream);
 
 /* ------------------------------------------------------------------------ */
+/* Proposal-target assignment                              */
+/* replaces the device part of _ProposalTargetLayer.forward                   */
+/*   lib/model/rpn/proposal_target_layer_cascade.py:118-130 (overlaps, max,   */
+/*   gt class), :183-212 (gather, label clamp, targets, weights).             */
+/* The fg / bg sampling (:140-181) stays on the host with numpy's RNG.        */
+/* ------------------------------------------------------------------------ */
+/* rois (batch, n, roi_stride) with x1,y1,x2,y2 at column roi_offset (the layer passes the
+ * proposals with the gt boxes appended: stride 5, offset 1); gt (batch, k, gt_stride >= 5)
+ * = [x1,y1,x2,y2,class].  max_overlaps / labels (batch, n) fp32, assignment (batch, n) int32
+ * (ties -> lowest gt index); labels = class of the assigned gt box. */
+int tlod_roi_gt_assign(const float* rois, int roi_stride, int roi_offset, const float* gt,
+                       int gt_stride, float* max_overlaps, int* assignment, float* labels, int batch,
+                       int n, int k, void* stream);
+/* keep (batch, rois_per_image) int32: sampled candidate indices, foreground first;
+ * fg_count (batch) int32: rows >= fg_count[b] get label 0.  Outputs: rois_out
+ * (batch, P, 5) with column 0 = image index, labels_out (batch, P), targets_out / inside_out /
+ * outside_out (batch, P, 4); targets = bbox_transform_batch(roi, assigned gt), optionally
+ * (t - h_means) / h_stds, zero where label == 0.  h_* are HOST pointers to 4 floats. */
+int tlod_proposal_targets(const float* rois, int roi_stride, int roi_offset, const float* gt,
+                          int gt_stride, const int* assignment, const float* labels, const int* keep,
+                          const int* fg_count, float* rois_out, float* labels_out, float* targets_out,
+                          float* inside_out, float* outside_out, int batch, int n, int k,
+                          int rois_per_image, const float* h_means, const float* h_stds,
+                          const float* h_inside_w, int normalize, void* stream);
+
+/* ------------------------------------------------------------------------ */
 /* Gradient reversal + domain-classifier loss reduction                       */
 /*   lib/DAF/DA.py:19-33 (GRLayer), lib/MAF/DA.py:34-53 (weighted GRL),       */
 /*   lib/DAF/faster_rcnn.py:181-220 (image / instance / consistency losses)   */

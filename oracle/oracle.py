@@ -122,6 +122,66 @@ def roi_pool_backward(top_grad, argmax, rois, feature_shape, spatial_scale):
 
 
 # ---------------------------------------------------------------------------
+# _ProposalTargetLayer   (lib/model/rpn/proposal_target_layer_cascade.py:33-212)
+# ---------------------------------------------------------------------------
+def proposal_target_layer(all_rois, gt_boxes, rng=np.random, batch_size=128, fg_fraction=0.25, fg_thresh=0.5,
+                          bg_thresh_hi=0.5, bg_thresh_lo=0.1, means=(0.0, 0.0, 0.0, 0.0),
+                          stds=(0.1, 0.1, 0.2, 0.2), inside_weights=(1.0, 1.0, 1.0, 1.0), normalize=True):
+    """all_rois (B, N, 5), gt_boxes (B, K, 5) -> (rois, labels, bbox_targets, inside_w, outside_w).
+    ``rng`` (permutation, rand) is consumed in exactly the reference's order (:140-181)."""
+    rois = np.asarray(all_rois, np.float32)
+    gt = np.asarray(gt_boxes, np.float32)
+    B = gt.shape[0]
+    app = np.zeros_like(gt)
+    app[:, :, 1:5] = gt[:, :, :4]
+    rois = np.concatenate([rois, app], 1)
+    P = int(batch_size)
+    fg_per = int(np.round(fg_fraction * P))
+    fg_per = 1 if fg_per == 0 else fg_per
+    ov = bbox_overlaps_batch(rois, gt)                      # (B, n, K); batched, column 0 dropped
+    max_ov = ov.max(2)
+    assign = ov.argmax(2)                                    # ties -> lowest index
+    labels = np.take_along_axis(gt[:, :, 4], assign, axis=1)
+    labels_b = np.zeros((B, P), np.float32)
+    rois_b = np.zeros((B, P, 5), np.float32)
+    gt_b = np.zeros((B, P, 5), np.float32)
+    for i in range(B):
+        fg = np.nonzero(max_ov[i] >= np.float32(fg_thresh))[0]
+        bg = np.nonzero((max_ov[i] < np.float32(bg_thresh_hi)) & (max_ov[i] >= np.float32(bg_thresh_lo)))[0]
+        if fg.size > 0 and bg.size > 0:
+            fg_this = min(fg_per, fg.size)
+            fg = fg[rng.permutation(fg.size)[:fg_this]]
+            bg = bg[np.floor(rng.rand(P - fg_this) * bg.size).astype(np.int64)]
+        elif fg.size > 0:
+            fg = fg[np.floor(rng.rand(P) * fg.size).astype(np.int64)]
+            fg_this = P
+            bg = bg[:0]
+        elif bg.size > 0:
+            bg = bg[np.floor(rng.rand(P) * bg.size).astype(np.int64)]
+            fg_this = 0
+            fg = fg[:0]
+        else:
+            raise ValueError("bg_num_rois = 0 and fg_num_rois = 0, this should not happen!")
+        keep = np.concatenate([fg, bg])
+        labels_b[i] = labels[i][keep]
+        if fg_this < P:
+            labels_b[i][fg_this:] = 0
+        rois_b[i] = rois[i][keep]
+        rois_b[i, :, 0] = i
+        gt_b[i] = gt[i][assign[i][keep]]
+    t = bbox_transform_batch(rois_b[:, :, 1:5], gt_b[:, :, :4])
+    if normalize:
+        t = (t - np.asarray(means, np.float32)) / np.asarray(stds, np.float32)
+    targets = np.zeros((B, P, 4), np.float32)
+    inside = np.zeros((B, P, 4), np.float32)
+    pos = labels_b > 0
+    targets[pos] = t[pos]
+    inside[pos] = np.asarray(inside_weights, np.float32)
+    outside = (inside > 0).astype(np.float32)
+    return rois_b, labels_b, targets, inside, outside
+
+
+# ---------------------------------------------------------------------------
 # RoICrop   (lib/model/roi_crop/src/roi_crop_cuda_kernel.cu:12-23, 45-108, 111-190)
 # ---------------------------------------------------------------------------
 def roi_crop_forward(features, grid_yx):

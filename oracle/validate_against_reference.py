@@ -18,7 +18,10 @@ Runs only in the build container (needs /root/reference).  It
    the reference's code.  The NMS / RoIPool / RoIAlign-backward restatements are
    pinned on the GPU box against the reference CUDA kernels recompiled unmodified
    (oracle/_ref/libref_cuda*.so; tests/test_gpu_reference_cuda.py).
-3. saves small golden vectors (inputs are regenerated from the seed in the tests;
+3. runs the reference's ``_ProposalTargetLayer`` (proposal_target_layer_cascade.py, with a
+   one-line ``Tensor.index`` shim for torch 2.x) under the same numpy seed and requires equality
+   of the sampled rois, labels, weights (bit-exact) and regression targets (log() within 2e-6);
+4. saves small golden vectors (inputs are regenerated from the seed in the tests;
    outputs are stored) under tests/golden/.
 
 Usage: python oracle/validate_against_reference.py [--no-write]
@@ -237,7 +240,46 @@ def main():
     gold_rpn["ties_deltas"] = deltas.numpy()
     gold_rpn["ties_exp"] = torch.exp(deltas).numpy()
 
+    # ---------------- 3. reference _ProposalTargetLayer ----------------------
+    # proposal_target_layer_cascade.py:133 calls Tensor.index((idx,)), which torch 2.x no longer has;
+    # the shim below is the only change (the reference source is used as it lies).
+    _orig_index = getattr(torch.Tensor, "index", None)  # torch 2.11 has an unrelated Tensor.index(idx, dims)
+    torch.Tensor.index = lambda self, idx, *a: self[idx]
+    import model.rpn.proposal_target_layer_cascade as ref_ptl
+    gold_pt = {}
+    for tag, (B, seed, batch, bg_lo) in {"default_cfg": (2, 21, 128, 0.1), "cityscape_yml": (3, 22, 256, 0.0)}.items():
+        A, H, W = 12, 37, 75
+        prob, deltas = synth_rpn(B, A, H, W, seed)
+        im_info = torch.tensor([[600.0, 1200.0, 0.5859375]] * B)
+        gt = synth_gt(B, 20, 50, seed + 50, im_h=600, im_w=1200)
+        rois = orc.proposal_layer(prob.numpy(), deltas.numpy(), im_info.numpy(), anchors12, 16, 12000, 2000, 0.7,
+                                  exp_deltas=torch.exp(deltas).numpy())
+        cfg.TRAIN.BATCH_SIZE, cfg.TRAIN.BG_THRESH_LO = batch, bg_lo
+        layer = ref_ptl._ProposalTargetLayer(9)
+        np.random.seed(3)
+        ref_o = layer(torch.from_numpy(rois), gt, torch.full((B,), 20, dtype=torch.long))
+        np.random.seed(3)
+        mine_o = orc.proposal_target_layer(rois, gt.numpy(), batch_size=batch, bg_thresh_lo=bg_lo)
+        for nm, a, b in zip(("rois", "labels", "bbox_targets", "inside_w", "outside_w"), mine_o, ref_o):
+            b = b.numpy()
+            if nm == "bbox_targets":
+                check("proposal_target bbox_targets dx,dy [%s]" % tag, a[:, :, :2], b[:, :, :2])
+                ok = np.allclose(a[:, :, 2:], b[:, :, 2:], rtol=2e-6, atol=2e-6)
+                print(("PASS " if ok else "FAIL ") + "proposal_target bbox_targets dw,dh (2e-6) [%s]" % tag)
+                if not ok:
+                    raise SystemExit(1)
+            else:
+                check("proposal_target %s [%s]" % (nm, tag), a, b)
+            gold_pt["%s_%s" % (tag, nm)] = b
+        gold_pt[tag + "_all_rois"] = rois
+        gold_pt[tag + "_gt"] = gt.numpy()
+        gold_pt[tag + "_cfg"] = np.array([batch, bg_lo], np.float64)
+    cfg.TRAIN.BATCH_SIZE, cfg.TRAIN.BG_THRESH_LO = 128, 0.1
+    if _orig_index is not None:
+        torch.Tensor.index = _orig_index
+
     if not args.no_write:
+        np.savez_compressed(os.path.join(GOLD, "proposal_target_ref_py.npz"), **gold_pt)
         np.savez_compressed(os.path.join(GOLD, "roi_align_ref_cpu.npz"), **gold_roi)
         np.savez_compressed(os.path.join(GOLD, "rpn_layers_ref_py.npz"), **gold_rpn)
         print("wrote", GOLD)

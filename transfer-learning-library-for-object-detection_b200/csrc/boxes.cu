@@ -7,6 +7,7 @@
 //   clip_boxes             lib/model/rpn/bbox_transform.py:125-133
 //   bbox_overlaps_batch    lib/model/rpn/bbox_transform.py:168-257
 //   _AnchorTargetLayer     lib/model/rpn/anchor_target_layer.py:98-116, :147-191
+//   _ProposalTargetLayer   lib/model/rpn/proposal_target_layer_cascade.py:33-57, :113-212
 #include <limits.h>
 
 #include "common.cuh"
@@ -239,6 +240,80 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---------------------------------------------------------------------------
+// _ProposalTargetLayer, device part 1 (proposal_target_layer_cascade.py:118-130):
+// per RoI the best-overlapping gt box (ties -> lowest index), that overlap and the gt's class.
+// rois (B, n, roi_stride) with the box at column roi_off; gt (B, k, >= 5).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    roi_gt_assign_kernel(const float* __restrict__ rois, int roi_stride, int roi_off,
+                         const float* __restrict__ gt, int gstride, float* __restrict__ max_overlaps,
+                         int* __restrict__ assignment, float* __restrict__ labels, int n, int k) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 a = load4(rois + ((size_t)b * n + i) * roi_stride + roi_off);
+  const float aw = __fadd_rn(__fsub_rn(a.z, a.x), 1.f), ah = __fadd_rn(__fsub_rn(a.w, a.y), 1.f);
+  const float aarea = __fmul_rn(aw, ah);
+  const bool azero = (aw == 1.f) && (ah == 1.f);
+  float best = -INFINITY;
+  int besti = 0;
+  for (int j = 0; j < k; ++j) {
+    const GtBox g = make_gt(gt + ((size_t)b * k + j) * gstride);
+    const float ov = pair_overlap(a, aarea, azero, g);
+    if (ov > best) {
+      best = ov;
+      besti = j;
+    }
+  }
+  const size_t o = (size_t)b * n + i;
+  max_overlaps[o] = best;
+  assignment[o] = besti;
+  labels[o] = __ldg(gt + ((size_t)b * k + besti) * gstride + 4);
+}
+
+// device part 2 (:183-212): gather the sampled RoIs, clamp background labels, encode and
+// normalise the regression targets, inside / outside weights.
+// keep (B, P) int32 indices into the n candidates; fg_count (B): positions >= fg_count[b] are
+// background.  rois_out (B, P, 5), labels_out (B, P), targets / inside / outside (B, P, 4).
+__global__ void __launch_bounds__(256)
+    proposal_targets_kernel(const float* __restrict__ rois, int roi_stride, int roi_off,
+                            const float* __restrict__ gt, int gstride, const int* __restrict__ assignment,
+                            const float* __restrict__ labels, const int* __restrict__ keep,
+                            const int* __restrict__ fg_count, float* __restrict__ rois_out,
+                            float* __restrict__ labels_out, float* __restrict__ targets_out,
+                            float* __restrict__ inside_out, float* __restrict__ outside_out, int n, int k,
+                            int P, float4 means, float4 stds, float4 inside_w, int normalize) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= P) return;
+  const int src = __ldg(keep + (size_t)b * P + j);
+  const size_t so = (size_t)b * n + src;
+  const float4 box = load4(rois + so * roi_stride + roi_off);
+  float lab = __ldg(labels + so);
+  if (j >= __ldg(fg_count + b)) lab = 0.f;  // :194-195
+  const float4 g = load4(gt + ((size_t)b * k + __ldg(assignment + so)) * gstride);
+  float4 t = encode_box(box, g);
+  if (normalize) {  // :106-109: (targets - means) / stds, each op rounded
+    t.x = __fdiv_rn(__fsub_rn(t.x, means.x), stds.x);
+    t.y = __fdiv_rn(__fsub_rn(t.y, means.y), stds.y);
+    t.z = __fdiv_rn(__fsub_rn(t.z, means.z), stds.z);
+    t.w = __fdiv_rn(__fsub_rn(t.w, means.w), stds.w);
+  }
+  const bool fg = lab > 0.f;
+  const size_t o = (size_t)b * P + j;
+  float* r = rois_out + o * 5;
+  r[0] = (float)b;
+  r[1] = box.x; r[2] = box.y; r[3] = box.z; r[4] = box.w;
+  labels_out[o] = lab;
+  const float4 tt = fg ? t : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 iw = fg ? inside_w : make_float4(0.f, 0.f, 0.f, 0.f);
+  reinterpret_cast<float4*>(targets_out)[o] = tt;
+  reinterpret_cast<float4*>(inside_out)[o] = iw;
+  reinterpret_cast<float4*>(outside_out)[o] =
+      make_float4(iw.x > 0.f ? 1.f : 0.f, iw.y > 0.f ? 1.f : 0.f, iw.z > 0.f ? 1.f : 0.f, iw.w > 0.f ? 1.f : 0.f);
+}
+
 }  // namespace tlod
 
 using namespace tlod;
@@ -360,6 +435,48 @@ extern "C" int tlod_anchor_targets_finalize(const float* labels, const int* argm
         labels, argmax, anchors, gt, gt_stride, inv_index, labels_out, targets_out, inside_w_out,
         outside_w_out, n, k, num_anchors, height, width, inside_weight, positive_weight,
         negative_weight);
+  }
+  return last_launch_status();
+}
+
+extern "C" int tlod_roi_gt_assign(const float* rois, int roi_stride, int roi_offset, const float* gt,
+                                  int gt_stride, float* max_overlaps, int* assignment, float* labels,
+                                  int batch, int n, int k, void* stream) {
+  if (!rois || !gt || !max_overlaps || !assignment || !labels) return TLOD_ERR_NULL_POINTER;
+  if (batch <= 0 || n <= 0 || k <= 0 || roi_stride < roi_offset + 4 || gt_stride < 5 || batch > 65535)
+    return TLOD_ERR_BAD_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  {
+    LaunchScope scope("roi_gt_assign_kernel", st);
+    roi_gt_assign_kernel<<<dim3((n + 255) / 256, batch), 256, 0, st>>>(rois, roi_stride, roi_offset, gt, gt_stride,
+                                                                    max_overlaps, assignment, labels, n, k);
+  }
+  return last_launch_status();
+}
+
+extern "C" int tlod_proposal_targets(const float* rois, int roi_stride, int roi_offset, const float* gt,
+                                     int gt_stride, const int* assignment, const float* labels,
+                                     const int* keep, const int* fg_count, float* rois_out,
+                                     float* labels_out, float* targets_out, float* inside_out,
+                                     float* outside_out, int batch, int n, int k, int rois_per_image,
+                                     const float* h_means, const float* h_stds, const float* h_inside_w,
+                                     int normalize, void* stream) {
+  if (!rois || !gt || !assignment || !labels || !keep || !fg_count || !rois_out || !labels_out ||
+      !targets_out || !inside_out || !outside_out || !h_means || !h_stds || !h_inside_w)
+    return TLOD_ERR_NULL_POINTER;
+  if (batch <= 0 || n <= 0 || k <= 0 || rois_per_image <= 0 || roi_stride < roi_offset + 4 || gt_stride < 5 ||
+      batch > 65535)
+    return TLOD_ERR_BAD_SHAPE;
+  if (((uintptr_t)targets_out | (uintptr_t)inside_out | (uintptr_t)outside_out) & 15) return TLOD_ERR_BAD_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float4 m = make_float4(h_means[0], h_means[1], h_means[2], h_means[3]);
+  const float4 sd = make_float4(h_stds[0], h_stds[1], h_stds[2], h_stds[3]);
+  const float4 iw = make_float4(h_inside_w[0], h_inside_w[1], h_inside_w[2], h_inside_w[3]);
+  {
+    LaunchScope scope("proposal_targets_kernel", st);
+    proposal_targets_kernel<<<dim3((rois_per_image + 255) / 256, batch), 256, 0, st>>>(
+        rois, roi_stride, roi_offset, gt, gt_stride, assignment, labels, keep, fg_count, rois_out, labels_out,
+        targets_out, inside_out, outside_out, n, k, rois_per_image, m, sd, iw, normalize);
   }
   return last_launch_status();
 }

@@ -1,0 +1,91 @@
+"""_ProposalTargetLayer (lib/model/rpn/proposal_target_layer_cascade.py:20-212).
+
+Same constructor (nclasses) and forward(all_rois, gt_boxes, num_boxes) ->
+(rois (B,P,5), labels (B,P), bbox_targets, bbox_inside_weights, bbox_outside_weights (B,P,4)).
+
+Device work is two launches (tlod_roi_gt_assign: IoU + row max / argmax + class of the assigned gt,
+no (B,N,K) tensor; tlod_proposal_targets: gather + label clamp + target encode / normalise +
+weights).  The fg / bg sampling stays on the host with numpy's global RNG, consumed in exactly the
+reference's order (:140-181: ``permutation`` for the foreground, ``rand`` for the background),
+on one pinned copy of the (B, n) max-overlap array; the reference synchronises per image and
+runs a Python double loop over the sampled RoIs (:83-91)."""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from model.utils.config import cfg
+from tlod_b200 import functional as F
+
+
+class _ProposalTargetLayer(nn.Module):
+    def __init__(self, nclasses):
+        super(_ProposalTargetLayer, self).__init__()
+        self._num_classes = nclasses
+        self._host = None
+
+    def forward(self, all_rois, gt_boxes, num_boxes):
+        B, K = gt_boxes.size(0), gt_boxes.size(1)
+        dev = gt_boxes.device
+        # :42-46 -- ground-truth boxes join the candidates (class column dropped, image index 0)
+        gt_append = gt_boxes.new_zeros(gt_boxes.size())
+        gt_append[:, :, 1:5] = gt_boxes[:, :, :4]
+        all_rois = torch.cat([all_rois, gt_append], 1).contiguous()
+        n = all_rois.size(1)
+
+        num_images = 1
+        rois_per_image = int(cfg.TRAIN.BATCH_SIZE / num_images)
+        fg_rois_per_image = int(np.round(cfg.TRAIN.FG_FRACTION * rois_per_image))
+        fg_rois_per_image = 1 if fg_rois_per_image == 0 else fg_rois_per_image
+
+        max_overlaps, assignment, labels = F.roi_gt_assign(all_rois, gt_boxes)
+        if self._host is None or self._host.shape != max_overlaps.shape:
+            self._host = torch.empty(max_overlaps.shape, dtype=torch.float32).pin_memory()
+        self._host.copy_(max_overlaps, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        mo = self._host.numpy()
+
+        # ---- host-side sampling, :140-181: same index order, same RNG calls ----
+        keep = np.empty((B, rois_per_image), np.int32)
+        fg_count = np.empty((B,), np.int32)
+        fg_thresh = np.float32(cfg.TRAIN.FG_THRESH)
+        bg_hi, bg_lo = np.float32(cfg.TRAIN.BG_THRESH_HI), np.float32(cfg.TRAIN.BG_THRESH_LO)
+        for i in range(B):
+            fg_inds = np.nonzero(mo[i] >= fg_thresh)[0]
+            bg_inds = np.nonzero((mo[i] < bg_hi) & (mo[i] >= bg_lo))[0]
+            fg_num, bg_num = fg_inds.shape[0], bg_inds.shape[0]
+            if fg_num > 0 and bg_num > 0:
+                fg_this = min(fg_rois_per_image, fg_num)
+                rand_num = np.random.permutation(fg_num)
+                fg_inds = fg_inds[rand_num[:fg_this]]
+                bg_this = rois_per_image - fg_this
+                rand_num = np.floor(np.random.rand(bg_this) * bg_num).astype(np.int64)
+                bg_inds = bg_inds[rand_num]
+            elif fg_num > 0 and bg_num == 0:
+                rand_num = np.floor(np.random.rand(rois_per_image) * fg_num).astype(np.int64)
+                fg_inds = fg_inds[rand_num]
+                fg_this = rois_per_image
+                bg_inds = bg_inds[:0]
+            elif bg_num > 0 and fg_num == 0:
+                rand_num = np.floor(np.random.rand(rois_per_image) * bg_num).astype(np.int64)
+                bg_inds = bg_inds[rand_num]
+                fg_this = 0
+                fg_inds = fg_inds[:0]
+            else:
+                raise ValueError("bg_num_rois = 0 and fg_num_rois = 0, this should not happen!")
+            keep[i] = np.concatenate([fg_inds, bg_inds])
+            fg_count[i] = fg_this
+
+        keep_d = torch.from_numpy(keep).to(dev, non_blocking=True)
+        fg_d = torch.from_numpy(fg_count).to(dev, non_blocking=True)
+        rois, labels_b, targets, inside, outside = F.proposal_targets(
+            all_rois, gt_boxes, assignment, labels, keep_d, fg_d, cfg.TRAIN.BBOX_NORMALIZE_MEANS,
+            cfg.TRAIN.BBOX_NORMALIZE_STDS, cfg.TRAIN.BBOX_INSIDE_WEIGHTS,
+            cfg.TRAIN.BBOX_NORMALIZE_TARGETS_PRECOMPUTED)
+        return rois, labels_b, targets, inside, outside
+
+    def backward(self, top, propagate_down, bottom):
+        """This layer does not propagate gradients."""
+        pass
+
+    def reshape(self, bottom, top):
+        pass

@@ -37,6 +37,16 @@ __C.TRAIN.RPN_MIN_SIZE = 8                # :148 (read, unused: proposal_layer.p
 __C.TRAIN.RPN_BBOX_INSIDE_WEIGHTS = (1.0, 1.0, 1.0, 1.0)  # :150
 __C.TRAIN.RPN_POSITIVE_WEIGHT = -1.0      # :154
 
+__C.TRAIN.BATCH_SIZE = 128                # config.py:76 (cfgs/vgg16.yml, res101.yml: 256 / 128)
+__C.TRAIN.FG_FRACTION = 0.25              # :79
+__C.TRAIN.FG_THRESH = 0.5                 # :82
+__C.TRAIN.BG_THRESH_HI = 0.5              # :86
+__C.TRAIN.BG_THRESH_LO = 0.1              # :87 (cfgs set 0.0)
+__C.TRAIN.BBOX_NORMALIZE_TARGETS_PRECOMPUTED = True  # :117
+__C.TRAIN.BBOX_NORMALIZE_MEANS = (0.0, 0.0, 0.0, 0.0)  # :118
+__C.TRAIN.BBOX_NORMALIZE_STDS = (0.1, 0.1, 0.2, 0.2)   # :119
+__C.TRAIN.BBOX_INSIDE_WEIGHTS = (1.0, 1.0, 1.0, 1.0)   # :114
+
 __C.TEST = AttrDict()
 __C.TEST.NMS = 0.3
 __C.TEST.RPN_NMS_THRESH = 0.7             # :193

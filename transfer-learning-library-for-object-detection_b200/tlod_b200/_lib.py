@@ -51,6 +51,10 @@ SIGNATURES = {
                                    P, c_size_t, P]),
     "tlod_anchor_targets_finalize": (c_int, [P, P, P, P, c_int, P, P, P, P, P, c_int, c_int, c_int, c_int,
                                              c_int, c_int, c_float, c_float, c_float, P]),
+    "tlod_roi_gt_assign": (c_int, [P, c_int, c_int, P, c_int, P, P, P, c_int, c_int, c_int, P]),
+    "tlod_proposal_targets": (c_int, [P, c_int, c_int, P, c_int, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int,
+                                      c_int, ctypes.POINTER(c_float), ctypes.POINTER(c_float),
+                                      ctypes.POINTER(c_float), c_int, P]),
     "tlod_grl_backward": (c_int, [P, P, c_float, c_longlong, P]),
     "tlod_grl_backward_weighted": (c_int, [P, P, P, c_float, c_int, c_int, P]),
     "tlod_da_loss_workspace_bytes": (c_size_t, []),

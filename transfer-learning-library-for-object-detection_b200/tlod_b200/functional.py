@@ -6,6 +6,7 @@ them synchronises the host.  A CPU tensor is an error -- there is no CPU path.
 """
 from __future__ import annotations
 
+import ctypes
 from typing import Optional, Tuple
 
 import torch
@@ -345,6 +346,52 @@ def anchor_targets_finalize(labels, argmax, anchors, gt_boxes, inv_index, num_an
                                                float(negative_weight), _stream(dev)),
               "tlod_anchor_targets_finalize")
     return labels_out, targets, inside, outside
+
+
+# ---------------------------------------------------------------------------
+# proposal targets
+# ---------------------------------------------------------------------------
+def roi_gt_assign(all_rois, gt_boxes):
+    """all_rois (B, n, 5) [image, x1, y1, x2, y2], gt (B, K, 5) -> (max_overlaps (B,n) f32,
+    assignment (B,n) int32, labels (B,n) f32 = class of the assigned gt)."""
+    _require_cuda(all_rois, gt_boxes)
+    rois, gt = _f32(all_rois), _f32(gt_boxes)
+    B, n, rs = rois.shape
+    K, gs = gt.size(1), gt.size(2)
+    dev = rois.device
+    mx = torch.empty((B, n), dtype=torch.float32, device=dev)
+    asg = torch.empty((B, n), dtype=torch.int32, device=dev)
+    lab = torch.empty((B, n), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.tlod_roi_gt_assign(rois.data_ptr(), rs, 1 if rs == 5 else 0, gt.data_ptr(), gs, mx.data_ptr(),
+                                     asg.data_ptr(), lab.data_ptr(), B, n, K, _stream(dev)), "tlod_roi_gt_assign")
+    return mx, asg, lab
+
+
+def proposal_targets(all_rois, gt_boxes, assignment, labels, keep, fg_count, means, stds, inside_weights,
+                     normalize: bool):
+    _require_cuda(all_rois, gt_boxes, assignment, labels, keep, fg_count)
+    rois, gt, labels = _f32(all_rois), _f32(gt_boxes), _f32(labels)
+    assignment, keep, fg_count = assignment.contiguous(), keep.contiguous(), fg_count.contiguous()
+    B, n, rs = rois.shape
+    K, gs = gt.size(1), gt.size(2)
+    P = keep.size(1)
+    dev = rois.device
+    rois_out = torch.empty((B, P, 5), dtype=torch.float32, device=dev)
+    labels_out = torch.empty((B, P), dtype=torch.float32, device=dev)
+    targets = torch.empty((B, P, 4), dtype=torch.float32, device=dev)
+    inside = torch.empty_like(targets)
+    outside = torch.empty_like(targets)
+    f4 = ctypes.c_float * 4
+    with torch.cuda.device(dev):
+        check(lib.tlod_proposal_targets(rois.data_ptr(), rs, 1 if rs == 5 else 0, gt.data_ptr(), gs,
+                                        assignment.data_ptr(), labels.data_ptr(), keep.data_ptr(),
+                                        fg_count.data_ptr(), rois_out.data_ptr(), labels_out.data_ptr(),
+                                        targets.data_ptr(), inside.data_ptr(), outside.data_ptr(), B, n, K, P,
+                                        f4(*[float(v) for v in means]), f4(*[float(v) for v in stds]),
+                                        f4(*[float(v) for v in inside_weights]), int(bool(normalize)),
+                                        _stream(dev)), "tlod_proposal_targets")
+    return rois_out, labels_out, targets, inside, outside
 
 
 # ---------------------------------------------------------------------------
