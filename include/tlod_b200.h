@@ -172,6 +172,24 @@ size_t tlod_nms_workspace_bytes(int n);
 int tlod_nms(const float* boxes, int n, int box_stride, float thresh, int max_keep, int* keep_out,
              int* num_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Test-time per-class NMS of one image, all classes in one call:
+ * replaces the loop methods/DAF/DAF_test.py:302-320 (identical in every *_test.py):
+ *   for j in 1..K-1: inds = scores[:, j] > thresh; sort desc; nms(cls_dets, cfg.TEST.NMS).
+ * scores (num_rois, num_classes); boxes (num_rois, box_cols) with box_cols = 4 * num_classes
+ * (class j at columns 4j..4j+3) or 4 (class agnostic).  Classes first_class .. num_classes-1 are
+ * processed; c below = class - first_class; Rp = tlod_class_nms_padded_rows(num_rois).
+ * Outputs (device): dets_out (nc, Rp, 5) candidates sorted by score (ties: lower row first)
+ * = [x1, y1, x2, y2, score]; order_out (nc, Rp) their source rows (-1 = filler);
+ * count_out (nc) candidates above the threshold; keep_out (nc, Rp) kept positions, ascending;
+ * valid_out (nc): the class's detections are dets_out[c][keep_out[c][0 .. valid_out[c])].
+ * num_out (nc) is scratch.  num_rois <= 2048.  No host synchronisation inside. */
+int tlod_class_nms_padded_rows(int num_rois);
+size_t tlod_class_nms_workspace_bytes(int num_rois, int num_classes);
+int tlod_class_nms(const float* scores, const float* boxes, int num_rois, int num_classes,
+                   int first_class, int box_cols, float score_thresh, float nms_thresh, float* dets_out,
+                   int* order_out, int* keep_out, int* num_out, int* count_out, int* valid_out,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------ */
 /* Proposal layer (fused, batched)                                            */
 /* replaces _ProposalLayer.forward     lib/model/rpn/proposal_layer.py:49-163 */

@@ -122,6 +122,30 @@ def roi_pool_backward(top_grad, argmax, rois, feature_shape, spatial_scale):
 
 
 # ---------------------------------------------------------------------------
+# test-time per-class NMS   (methods/DAF/DAF_test.py:302-320, same in every *_test.py)
+# ---------------------------------------------------------------------------
+def per_class_nms(scores, pred_boxes, score_thresh, nms_thresh, first_class=1):
+    """scores (R, K), pred_boxes (R, 4K) or (R, 4) -> list of (n_j, 5) arrays for classes
+    first_class..K-1.  Sort = score descending, lower row first on ties (the reference's
+    torch.sort leaves tie order unspecified)."""
+    sc = np.asarray(scores, np.float32)
+    bx = np.asarray(pred_boxes, np.float32)
+    out = []
+    for j in range(first_class, sc.shape[1]):
+        inds = np.nonzero(sc[:, j] > np.float32(score_thresh))[0]
+        if inds.size == 0:
+            out.append(np.zeros((0, 5), np.float32))
+            continue
+        cls_scores = sc[inds, j]
+        order = np.argsort(-cls_scores.astype(np.float64), kind="stable")
+        cls_boxes = bx[inds] if bx.shape[1] == 4 else bx[inds][:, j * 4:(j + 1) * 4]
+        dets = np.concatenate([cls_boxes, cls_scores[:, None]], 1)[order]
+        keep = nms(dets, nms_thresh)
+        out.append(np.ascontiguousarray(dets[keep]))
+    return out
+
+
+# ---------------------------------------------------------------------------
 # _ProposalTargetLayer   (lib/model/rpn/proposal_target_layer_cascade.py:33-212)
 # ---------------------------------------------------------------------------
 def proposal_target_layer(all_rois, gt_boxes, rng=np.random, batch_size=128, fg_fraction=0.25, fg_thresh=0.5,

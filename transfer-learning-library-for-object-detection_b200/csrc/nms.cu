@@ -602,6 +602,95 @@ __global__ void __launch_bounds__(TK_THREADS)
 }
 
 // ===========================================================================
+// test-time per-class NMS, all classes of an image at once
+// ===========================================================================
+// methods/DAF/DAF_test.py:302-320 (same loop in every *_test.py): for each class j >= 1 keep the
+// detections with score > thresh, sort them by score, run nms(cfg.TEST.NMS) -- 8 sort + nms +
+// .cpu() rounds per image in the reference.  Here one CTA per class selects and sorts its
+// candidates (score descending, row index ascending on ties) and writes them as one "image" of a
+// batched NMS; rows that fail the threshold become far-away unit boxes behind the real ones, so
+// the batched mask / scan kernels run unchanged and the real survivors are the prefix of the keep
+// list with index < count.
+constexpr int CN_THREADS = 1024;
+constexpr int CN_MAXR = 2048;
+
+__global__ void __launch_bounds__(CN_THREADS)
+    class_sort_kernel(const float* __restrict__ scores, const float* __restrict__ boxes, int R, int K,
+                      int first_class, int box_cols, float score_thresh, int Rp,
+                      float* __restrict__ dets_out, int* __restrict__ order_out, int* __restrict__ count_out) {
+  __shared__ unsigned long long buf[CN_MAXR];
+  __shared__ int cnt;
+  const int cls = first_class + blockIdx.x, tid = threadIdx.x;
+  if (tid == 0) cnt = 0;
+  __syncthreads();
+  int mine = 0;
+  for (int r = tid; r < Rp; r += CN_THREADS) {
+    unsigned long long key = ~0ULL;
+    if (r < R) {
+      const float sc = __ldg(scores + (size_t)r * K + cls);
+      if (sc > score_thresh) {  // NaN fails, as in the reference's `scores[:, j] > thresh`
+        key = ((unsigned long long)(~score_key(sc)) << 32) | (unsigned)r;
+        ++mine;
+      }
+    }
+    buf[r] = key;
+  }
+  if (mine) atomicAdd(&cnt, mine);
+  __syncthreads();
+  for (int k = 2; k <= Rp; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < (Rp >> 1); t += CN_THREADS) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int l = i | j;
+        const unsigned long long x = buf[i], y = buf[l];
+        if ((x > y) == ((i & k) == 0)) {
+          buf[i] = y;
+          buf[l] = x;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  const int n = cnt;
+  float* d = dets_out + (size_t)blockIdx.x * Rp * 5;
+  for (int r = tid; r < Rp; r += CN_THREADS) {
+    float4 b;
+    float sc;
+    int src = -1;
+    if (r < n) {
+      src = (int)(unsigned)buf[r];
+      const float* bp = boxes + (size_t)src * box_cols + (box_cols > 4 ? cls * 4 : 0);
+      b = make_float4(__ldg(bp), __ldg(bp + 1), __ldg(bp + 2), __ldg(bp + 3));
+      sc = __ldg(scores + (size_t)src * K + cls);
+    } else {  // filler: unit boxes far from everything and from each other (IoU 0 with all)
+      const float x = 3.0e7f + 1024.f * (float)r;
+      b = make_float4(x, 3.0e7f, x, 3.0e7f);
+      sc = -INFINITY;
+    }
+    d[r * 5 + 0] = b.x; d[r * 5 + 1] = b.y; d[r * 5 + 2] = b.z; d[r * 5 + 3] = b.w; d[r * 5 + 4] = sc;
+    order_out[(size_t)blockIdx.x * Rp + r] = src;
+  }
+  if (tid == 0) count_out[blockIdx.x] = n;
+}
+
+// valid_out[c] = survivors that are real detections = keep entries < count (they form a prefix)
+__global__ void class_valid_kernel(const int* __restrict__ keep, const int* __restrict__ num,
+                                   const int* __restrict__ count, int Rp, int* __restrict__ valid_out) {
+  const int c = blockIdx.x;
+  int v = 0;
+  for (int i = threadIdx.x; i < num[c]; i += blockDim.x) v += keep[(size_t)c * Rp + i] < count[c] ? 1 : 0;
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  __shared__ int s[32];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s[w];
+    valid_out[c] = t;
+  }
+}
+
+// ===========================================================================
 // host side
 // ===========================================================================
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -749,4 +838,53 @@ extern "C" int tlod_proposals(const float* scores, const float* deltas, const fl
   if (rc) return rc;
   return launch_mask_scan(boxes, batch, n, 4, nms_thresh, post_nms_topN, mask, keep, post_nms_topN,
                           num, rois_out, post_nms_topN, (NmsState*)(base + w.state), st);
+}
+
+static int cn_pow2(int r) {
+  int p = 64;
+  while (p < r) p <<= 1;
+  return p;
+}
+
+extern "C" int tlod_class_nms_padded_rows(int num_rois) { return num_rois > 0 ? cn_pow2(num_rois) : 0; }
+
+extern "C" size_t tlod_class_nms_workspace_bytes(int num_rois, int num_classes) {
+  if (num_rois <= 0 || num_classes <= 0) return 256;
+  const int Rp = cn_pow2(num_rois);
+  return align_up((size_t)num_classes * Rp * nms_row_words(Rp) * 8, 256) +
+         align_up((size_t)num_classes * sizeof(NmsState), 256) + 256;
+}
+
+extern "C" int tlod_class_nms(const float* scores, const float* boxes, int num_rois, int num_classes,
+                              int first_class, int box_cols, float score_thresh, float nms_thresh,
+                              float* dets_out, int* order_out, int* keep_out, int* num_out, int* count_out,
+                              int* valid_out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!scores || !boxes || !dets_out || !order_out || !keep_out || !num_out || !count_out || !valid_out)
+    return TLOD_ERR_NULL_POINTER;
+  if (num_rois <= 0 || num_classes <= 0 || first_class < 0 || first_class >= num_classes ||
+      (box_cols != 4 && box_cols != 4 * num_classes))
+    return TLOD_ERR_BAD_SHAPE;
+  if (num_rois > CN_MAXR) return TLOD_ERR_UNSUPPORTED;
+  if (!workspace || workspace_bytes < tlod_class_nms_workspace_bytes(num_rois, num_classes) ||
+      ((uintptr_t)workspace & 31))
+    return TLOD_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Rp = cn_pow2(num_rois), nc = num_classes - first_class;
+  unsigned char* base = (unsigned char*)workspace;
+  unsigned long long* mask = (unsigned long long*)base;
+  NmsState* state = (NmsState*)(base + align_up((size_t)num_classes * Rp * nms_row_words(Rp) * 8, 256));
+  {
+    LaunchScope scope("class_sort_kernel", st);
+    class_sort_kernel<<<nc, CN_THREADS, 0, st>>>(scores, boxes, num_rois, num_classes, first_class, box_cols,
+                                                 score_thresh, Rp, dets_out, order_out, count_out);
+  }
+  int rc = last_launch_status();
+  if (rc) return rc;
+  rc = launch_mask_scan(dets_out, nc, Rp, 5, nms_thresh, Rp, mask, keep_out, Rp, num_out, nullptr, 0, state, st);
+  if (rc) return rc;
+  {
+    LaunchScope scope("class_valid_kernel", st);
+    class_valid_kernel<<<nc, 128, 0, st>>>(keep_out, num_out, count_out, Rp, valid_out);
+  }
+  return last_launch_status();
 }

@@ -38,6 +38,10 @@ SIGNATURES = {
     "tlod_roi_crop_backward": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "tlod_nms_workspace_bytes": (c_size_t, [c_int]),
     "tlod_nms": (c_int, [P, c_int, c_int, c_float, c_int, P, P, P, c_size_t, P]),
+    "tlod_class_nms_padded_rows": (c_int, [c_int]),
+    "tlod_class_nms_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "tlod_class_nms": (c_int, [P, P, c_int, c_int, c_int, c_int, c_float, c_float, P, P, P, P, P, P, P, c_size_t,
+                               P]),
     "tlod_proposals_n_sorted": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "tlod_proposals_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "tlod_proposals": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,

@@ -210,6 +210,33 @@ def nms_device(dets, thresh: float, max_keep: int = 0) -> Tuple[torch.Tensor, to
     return keep, num
 
 
+def class_nms(scores, pred_boxes, score_thresh: float, nms_thresh: float, first_class: int = 1):
+    """Per-class test-time NMS of one image (methods/*/*_test.py loop), all classes in one call.
+    scores (R, K), pred_boxes (R, 4K) or (R, 4) -> list over classes first_class..K-1 of
+    (n_j, 5) tensors [x1, y1, x2, y2, score] on the device.  One host synchronisation (the
+    per-class counts) instead of the reference's one per class."""
+    _require_cuda(scores, pred_boxes)
+    scores, boxes = _f32(scores), _f32(pred_boxes)
+    R, K = scores.shape
+    dev = scores.device
+    nc = K - first_class
+    if R == 0 or nc <= 0:
+        return [scores.new_zeros((0, 5)) for _ in range(max(nc, 0))]
+    Rp = lib.tlod_class_nms_padded_rows(R)
+    dets = torch.empty((nc, Rp, 5), dtype=torch.float32, device=dev)
+    order = torch.empty((nc, Rp), dtype=torch.int32, device=dev)
+    keep = torch.empty((nc, Rp), dtype=torch.int32, device=dev)
+    meta = torch.empty((3, nc), dtype=torch.int32, device=dev)  # num, count, valid
+    ws = _workspace(dev, lib.tlod_class_nms_workspace_bytes(R, K), "class_nms")
+    with torch.cuda.device(dev):
+        check(lib.tlod_class_nms(scores.data_ptr(), boxes.data_ptr(), R, K, int(first_class), boxes.size(1),
+                                 float(score_thresh), float(nms_thresh), dets.data_ptr(), order.data_ptr(),
+                                 keep.data_ptr(), meta[0].data_ptr(), meta[1].data_ptr(), meta[2].data_ptr(),
+                                 ws.data_ptr(), ws.numel(), _stream(dev)), "tlod_class_nms")
+    valid = meta[2].tolist()  # the one synchronisation
+    return [dets[c].index_select(0, keep[c, :valid[c]].long()) for c in range(nc)]
+
+
 def proposals(scores, deltas, im_info, anchors, feat_stride: int, pre_nms_topN: int, post_nms_topN: int,
               nms_thresh: float, return_debug: bool = False):
     """Fused batched proposal layer -> rois (B, post_nms_topN, 5)."""
