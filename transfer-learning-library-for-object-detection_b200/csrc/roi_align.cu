@@ -583,13 +583,13 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, un
 
 struct BwdState {
   float cw0[8], cw1[8], ms[8], mh[8];
-  int soff[16];
+  unsigned sa[16];  // shared-window address of site j in band row 0 of this lane's plane; ~0u = off
   int all_jump;
   int n;
 };
 
 // per-RoI column state from the stage's metadata block (all lanes read the same 208 bytes)
-__device__ __forceinline__ void bw_load_cols(BwdState& s, const float4* __restrict__ q) {
+__device__ __forceinline__ void bw_load_cols(BwdState& s, const float4* __restrict__ q, unsigned plane_addr) {
   float4 v[13];
 #pragma unroll
   for (int i = 0; i < 13; ++i) v[i] = q[i];
@@ -602,74 +602,47 @@ __device__ __forceinline__ void bw_load_cols(BwdState& s, const float4* __restri
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    s.soff[4 * i] = __float_as_int(v[8 + i].x); s.soff[4 * i + 1] = __float_as_int(v[8 + i].y);
-    s.soff[4 * i + 2] = __float_as_int(v[8 + i].z); s.soff[4 * i + 3] = __float_as_int(v[8 + i].w);
+    const int o[4] = {__float_as_int(v[8 + i].x), __float_as_int(v[8 + i].y), __float_as_int(v[8 + i].z),
+                      __float_as_int(v[8 + i].w)};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s.sa[4 * i + k] = o[k] < 0 ? 0xffffffffu : plane_addr + (unsigned)o[k];
   }
   s.all_jump = __float_as_int(v[12].x);
 }
 
-// predicated (branch-free) shared-memory access: active iff off >= 0
-__device__ __forceinline__ float lds_if(unsigned addr, int off) {
-  float v = 0.f;
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %2, 0;\n\t@p ld.shared.f32 %0, [%1];\n\t}"
-               : "+f"(v) : "r"(addr), "r"(off));
+// shared-memory access at [addr + IMM]; the _if forms are predicated on addr != ~0u (branch-free)
+template <int IMM>
+__device__ __forceinline__ float lds_at(unsigned addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(IMM));
   return v;
 }
-__device__ __forceinline__ void sts_if(unsigned addr, int off, float v) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %2, 0;\n\t@p st.shared.f32 [%1], %0;\n\t}"
-               :: "f"(v), "r"(addr), "r"(off) : "memory");
+template <int IMM>
+__device__ __forceinline__ void sts_at(unsigned addr, float v) {
+  asm volatile("st.shared.f32 [%0+%1], %2;" ::"r"(addr), "n"(IMM), "f"(v) : "memory");
 }
-__device__ __forceinline__ void sts_f32(unsigned addr, float v) {
-  asm volatile("st.shared.f32 [%0], %1;" :: "r"(addr), "f"(v) : "memory");
+template <int IMM>
+__device__ __forceinline__ float lds_at_if(unsigned addr) {
+  float v = 0.f;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0xffffffff;\n\t@p ld.shared.f32 %0, [%1+%2];\n\t}"
+               : "+f"(v) : "r"(addr), "n"(IMM));
+  return v;
+}
+template <int IMM>
+__device__ __forceinline__ void sts_at_if(unsigned addr, float v) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0xffffffff;\n\t@p st.shared.f32 [%0+%1], %2;\n\t}"
+               :: "r"(addr), "n"(IMM), "f"(v) : "memory");
 }
 
-// Add rw0 * e into plane row y0 and rw1 * e into row y0 + 1 (rows outside the band have
-// do0 / do1 false).  e[j] is the value of site j.  All enabled cells of a row are distinct,
-// so all loads are issued first, then the stores.  ALLJ: all 16 sites are enabled.
+// Values of the 16 column sites of one gradient row: the chain of BwdCols (ALLJ: identity).
 template <bool ALLJ>
-__device__ __forceinline__ void bw_rmw_rows(unsigned row0, unsigned row1, bool do0, bool do1, float rw0,
-                                            float rw1, const BwdState& s, const float (&e)[16]) {
-  float o0[16], o1[16];
-  if (do0) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j)
-      o0[j] = ALLJ ? lds_f32(row0 + (unsigned)s.soff[j]) : lds_if(row0 + (unsigned)s.soff[j], s.soff[j]);
-  }
-  if (do1) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j)
-      o1[j] = ALLJ ? lds_f32(row1 + (unsigned)s.soff[j]) : lds_if(row1 + (unsigned)s.soff[j], s.soff[j]);
-  }
-  if (do0) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float v = fmaf(rw0, e[j], o0[j]);
-      if (ALLJ) sts_f32(row0 + (unsigned)s.soff[j], v); else sts_if(row0 + (unsigned)s.soff[j], s.soff[j], v);
-    }
-  }
-  if (do1) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float v = fmaf(rw1, e[j], o1[j]);
-      if (ALLJ) sts_f32(row1 + (unsigned)s.soff[j], v); else sts_if(row1 + (unsigned)s.soff[j], s.soff[j], v);
-    }
-  }
-}
-
-__device__ __forceinline__ void bw_item(unsigned plane_addr, int W, int y_lo, int y_hi,
-                                        const float (&g)[8], const float4 rowt, const BwdState& s) {
-  float e[16];
-  const int y0 = __float_as_int(rowt.w);
-  const bool in0 = y0 >= y_lo && y0 < y_hi, in1 = y0 + 1 >= y_lo && y0 + 1 < y_hi;
-  const unsigned row0 = plane_addr + 4u * (unsigned)((y0 - y_lo) * W);
-  const unsigned row1 = row0 + 4u * (unsigned)W;
-  if (s.all_jump) {
+__device__ __forceinline__ void bw_sites(const float (&g)[8], const BwdState& s, float (&e)[16]) {
+  if (ALLJ) {
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
       e[2 * t] = g[t] * s.cw0[t];
       e[2 * t + 1] = g[t] * s.cw1[t];
     }
-    bw_rmw_rows<true>(row0, row1, in0, in1, rowt.y, rowt.z, s, e);
   } else {
     float a0 = 0.f, a1 = 0.f;
 #pragma unroll
@@ -680,10 +653,105 @@ __device__ __forceinline__ void bw_item(unsigned plane_addr, int W, int y_lo, in
       a0 = na0;
     }
     e[14] = a0; e[15] = a1;
-    bw_rmw_rows<false>(row0, row1, in0, in1, rowt.y, rowt.z, s, e);
   }
 }
 
+// Add rw0 * e into band row IMM0 / 4W and rw1 * e into band row IMM1 / 4W (byte offsets from band
+// row 0 as compile-time immediates: no address arithmetic per access).  All enabled cells of a
+// row are distinct, so the loads of the old values are issued first -- before the site values are
+// even computed, so that the serial column chain runs under their latency -- then the stores.
+// ALLJ: all 16 sites are enabled (no predicates).
+template <bool ALLJ, bool DO0, bool DO1, int IMM0, int IMM1>
+__device__ __forceinline__ void bw_rmw_fixed(float rw0, float rw1, const BwdState& s, const float (&g)[8]) {
+  float o0[16], o1[16], e[16];
+  if (DO0) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o0[j] = ALLJ ? lds_at<IMM0>(s.sa[j]) : lds_at_if<IMM0>(s.sa[j]);
+  }
+  if (DO1) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o1[j] = ALLJ ? lds_at<IMM1>(s.sa[j]) : lds_at_if<IMM1>(s.sa[j]);
+  }
+  bw_sites<ALLJ>(g, s, e);
+  if (DO0) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float v = fmaf(rw0, e[j], o0[j]);
+      if (ALLJ) sts_at<IMM0>(s.sa[j], v); else sts_at_if<IMM0>(s.sa[j], v);
+    }
+  }
+  if (DO1) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float v = fmaf(rw1, e[j], o1[j]);
+      if (ALLJ) sts_at<IMM1>(s.sa[j], v); else sts_at_if<IMM1>(s.sa[j], v);
+    }
+  }
+}
+
+// run-time row offsets (generic map widths / band heights): one add per access
+template <bool ALLJ>
+__device__ __forceinline__ void bw_rmw_dyn(unsigned off0, unsigned off1, bool do0, bool do1, float rw0,
+                                           float rw1, const BwdState& s, const float (&g)[8]) {
+  float o0[16], o1[16], e[16];
+  if (do0) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o0[j] = ALLJ ? lds_at<0>(s.sa[j] + off0) : (s.sa[j] != 0xffffffffu ? lds_at<0>(s.sa[j] + off0) : 0.f);
+  }
+  if (do1) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o1[j] = ALLJ ? lds_at<0>(s.sa[j] + off1) : (s.sa[j] != 0xffffffffu ? lds_at<0>(s.sa[j] + off1) : 0.f);
+  }
+  bw_sites<ALLJ>(g, s, e);
+  if (do0) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (ALLJ || s.sa[j] != 0xffffffffu) sts_at<0>(s.sa[j] + off0, fmaf(rw0, e[j], o0[j]));
+  }
+  if (do1) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (ALLJ || s.sa[j] != 0xffffffffu) sts_at<0>(s.sa[j] + off1, fmaf(rw1, e[j], o1[j]));
+  }
+}
+
+// W_T > 0: compile-time map width and band height BAND (1 or 2); W_T == 0: run-time geometry.
+template <bool ALLJ, int W_T, int BAND>
+__device__ __forceinline__ void bw_scatter(int W, int y_lo, int y_hi, const float4 rowt, const BwdState& s,
+                                           const float (&g)[8]) {
+  const int r0 = __float_as_int(rowt.w) - y_lo;  // band row of the first of the two plane rows
+  if (W_T > 0) {
+    constexpr int RB = 4 * W_T;
+    if (BAND == 2) {
+      if (r0 == 0) {
+        if (y_hi - y_lo == 2) bw_rmw_fixed<ALLJ, true, true, 0, RB>(rowt.y, rowt.z, s, g);
+        else bw_rmw_fixed<ALLJ, true, false, 0, RB>(rowt.y, rowt.z, s, g);  // last, one-row band
+      } else if (r0 < 0) {
+        bw_rmw_fixed<ALLJ, false, true, 0, 0>(rowt.y, rowt.z, s, g);
+      } else if (r0 < y_hi - y_lo) {
+        bw_rmw_fixed<ALLJ, true, false, RB, RB>(rowt.y, rowt.z, s, g);
+      }
+    } else {
+      if (r0 == 0) bw_rmw_fixed<ALLJ, true, false, 0, 0>(rowt.y, rowt.z, s, g);
+      else bw_rmw_fixed<ALLJ, false, true, 0, 0>(rowt.y, rowt.z, s, g);
+    }
+  } else {
+    const int rows = y_hi - y_lo;
+    bw_rmw_dyn<ALLJ>(4u * (unsigned)(r0 * W), 4u * (unsigned)((r0 + 1) * W), r0 >= 0 && r0 < rows,
+                     r0 + 1 >= 0 && r0 + 1 < rows, rowt.y, rowt.z, s, g);
+  }
+}
+
+template <int W_T, int BAND>
+__device__ __forceinline__ void bw_item(int W, int y_lo, int y_hi, const float (&g)[8], const float4 rowt,
+                                        const BwdState& s) {
+  if (s.all_jump)
+    bw_scatter<true, W_T, BAND>(W, y_lo, y_hi, rowt, s, g);
+  else
+    bw_scatter<false, W_T, BAND>(W, y_lo, y_hi, rowt, s, g);
+}
+
+template <int W_T, int BAND>
 __global__ void __launch_bounds__(BW_THREADS)
     roi_align_bwd_planes_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ bottom_grad,
                                 PlanPtrs pl, int B, int C, int H, int W, int AH, int ngroups,
@@ -791,11 +859,11 @@ __global__ void __launch_bounds__(BW_THREADS)
         const float4 gb = *reinterpret_cast<const float4*>(stg + r * 32 + (sw ^ 16));
         const float4* meta = reinterpret_cast<const float4*>(stg + BW_TILE_BYTES);
         const float4 rowt = meta[13];
-        if (nn != st.n) { bw_load_cols(st, meta); st.n = nn; }
+        if (nn != st.n) { bw_load_cols(st, meta, plane_addr); st.n = nn; }
         __syncwarp();
         if (lane == 0) mbar_arrive(&sh.empty_bar[s]);
         const float g[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
-        bw_item(plane_addr, W, y_lo, y_hi, g, rowt, st);
+        bw_item<W_T, BAND>(W, y_lo, y_hi, g, rowt, st);
       }
     }
     it0 += (unsigned)nitems;
@@ -995,15 +1063,17 @@ extern "C" int tlod_roi_align_backward(const float* top_grad, const float* rois,
                           sizeof(BWShared);
       const long long grid = (long long)batch * ngroups * nbands;
       if (grid <= 2147483647LL && smem <= (size_t)device_info().max_smem_optin) {
-        cudaError_t e = cudaFuncSetAttribute(roi_align_bwd_planes_kernel,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        // the 600x1200 / stride-16 maps (W = 75) with 1- or 2-row bands get compile-time row offsets
+        auto kern = roi_align_bwd_planes_kernel<0, 0>;
+        if (width == 75 && band_rows == 2) kern = roi_align_bwd_planes_kernel<75, 2>;
+        if (width == 75 && band_rows == 1) kern = roi_align_bwd_planes_kernel<75, 1>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         const PlanPtrs pl = plan_ptrs(const_cast<void*>(plan), batch, num_rois);
         {
           LaunchScope scope("roi_align_bwd_planes_kernel", st);
-          roi_align_bwd_planes_kernel<<<(int)grid, BW_THREADS, smem, st>>>(
-              tmap, bottom_grad, pl, batch, channels, height, width, aligned_h, ngroups, nbands,
-              band_rows, Sb);
+          kern<<<(int)grid, BW_THREADS, smem, st>>>(tmap, bottom_grad, pl, batch, channels, height, width,
+                                                   aligned_h, ngroups, nbands, band_rows, Sb);
         }
         return last_launch_status();
       }
