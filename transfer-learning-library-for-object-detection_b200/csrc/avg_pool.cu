@@ -12,11 +12,14 @@ constexpr int AP_SMEM_FLOATS = 8192;  // 32 KB of tiles per CTA pass
 
 // grid-stride over groups of T tiles.  FWD: in tile (AH, AW) -> out tile (AH-1, AW-1).
 // !FWD: in tile (AH-1, AW-1) (gradient of the pooled map) -> out tile (AH, AW).
-template <bool FWD>
+// AHT / AWT > 0: compile-time tile size (8 x 8 for RoIAlignAvg(7, 7): every division below
+// becomes a shift or a multiply); 0: run-time.
+template <bool FWD, int AHT, int AWT>
 __global__ void __launch_bounds__(AP_THREADS)
-    avgpool2x2_kernel(const float* __restrict__ in, float* __restrict__ out, long long tiles, int AH,
-                      int AW, int T) {
+    avgpool2x2_kernel(const float* __restrict__ in, float* __restrict__ out, long long tiles, int AH_rt,
+                      int AW_rt, int T) {
   extern __shared__ __align__(16) float sm[];
+  const int AH = AHT > 0 ? AHT : AH_rt, AW = AWT > 0 ? AWT : AW_rt;
   const int PH = AH - 1, PW = AW - 1;
   const int s_in = FWD ? AH * AW : PH * PW;
   const int s_out = FWD ? PH * PW : AH * AW;
@@ -74,10 +77,16 @@ static int launch_avgpool(bool fwd, const float* in, float* out, long long tiles
   const size_t smem = (size_t)T * s_big * sizeof(float);
   {
     LaunchScope scope(fwd ? "avgpool2x2_fwd_kernel" : "avgpool2x2_bwd_kernel", st);
-    if (fwd)
-      avgpool2x2_kernel<true><<<(unsigned)grid, AP_THREADS, smem, st>>>(in, out, tiles, ah, aw, T);
-    else
-      avgpool2x2_kernel<false><<<(unsigned)grid, AP_THREADS, smem, st>>>(in, out, tiles, ah, aw, T);
+    if (ah == 8 && aw == 8) {
+      if (fwd)
+        avgpool2x2_kernel<true, 8, 8><<<(unsigned)grid, AP_THREADS, smem, st>>>(in, out, tiles, ah, aw, T);
+      else
+        avgpool2x2_kernel<false, 8, 8><<<(unsigned)grid, AP_THREADS, smem, st>>>(in, out, tiles, ah, aw, T);
+    } else if (fwd) {
+      avgpool2x2_kernel<true, 0, 0><<<(unsigned)grid, AP_THREADS, smem, st>>>(in, out, tiles, ah, aw, T);
+    } else {
+      avgpool2x2_kernel<false, 0, 0><<<(unsigned)grid, AP_THREADS, smem, st>>>(in, out, tiles, ah, aw, T);
+    }
   }
   return last_launch_status();
 }
