@@ -96,7 +96,9 @@ class TlodStep(object):
         self.num_boxes = torch.full((N_SRC,), 20, dtype=torch.long)
         np.random.seed(3)
         self.graph = None
+        self.graphs = None
         self.static = None
+        self.streams = None
         self.launches_per_replay = 0
         self.host_out = None
         if use_graph:
@@ -121,10 +123,30 @@ class TlodStep(object):
         score.grad = None
         prob.grad = None
 
-    def device_part(self, d):
+    def device_part(self, d, copy_in=None, copy_out=None):
+        """Source and target domain are independent until the losses are summed: each runs on its
+        own stream (one CUDA graph per domain when captured), so the latency-bound kernels of one
+        domain can fill SMs the other leaves idle.  copy_in / copy_out (e2e mode) put each
+        domain's H2D / D2H copies on the same stream, overlapping the other domain's compute."""
         results = {}
-        self.domain("src", d, results)
-        self.domain("tgt", d, results)
+        cur = torch.cuda.current_stream(self.dev)
+        if self.streams is None:
+            self.streams = {"src": torch.cuda.Stream(self.dev), "tgt": torch.cuda.Stream(self.dev)}
+        for dom in ("src", "tgt"):
+            st = self.streams[dom]
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                if copy_in is not None:
+                    copy_in(dom)
+                if self.graphs is not None and d is self.d:
+                    self.graphs[dom].replay()
+                    results[dom] = self.static[dom]
+                else:
+                    self.domain(dom, d, results)
+                if copy_out is not None:
+                    copy_out(dom, results)
+        for dom in ("src", "tgt"):
+            cur.wait_stream(self.streams[dom])
         return results
 
     def anchor_part(self, d, results):
@@ -133,55 +155,71 @@ class TlodStep(object):
         return results
 
     def capture(self):
-        """Warm up on a side stream, then capture device_part() over the static inputs self.d."""
+        """Warm up on a side stream, then capture one CUDA graph per domain over the static inputs."""
         try:
             side = torch.cuda.Stream(self.dev)
             side.wait_stream(torch.cuda.current_stream(self.dev))
             with torch.cuda.stream(side):
                 for _ in range(3):
-                    self.device_part(self.d)
+                    r = {}
+                    self.domain("src", self.d, r)
+                    self.domain("tgt", self.d, r)
             torch.cuda.current_stream(self.dev).wait_stream(side)
             torch.cuda.synchronize(self.dev)
-            graph = torch.cuda.CUDAGraph()
+            graphs, static = {}, {}
             n0 = self.tlod.launch_count()
-            with torch.cuda.graph(graph):
-                static = self.device_part(self.d)
+            for dom in ("src", "tgt"):
+                graphs[dom] = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graphs[dom]):
+                    self.domain(dom, self.d, static)
             self.launches_per_replay = int(self.tlod.launch_count() - n0)
-            graph.replay()
+            for dom in ("src", "tgt"):
+                graphs[dom].replay()
             torch.cuda.synchronize(self.dev)
-            self.graph, self.static = graph, static
+            self.graphs, self.static = graphs, static
+            self.graph = graphs
         except Exception as e:  # noqa: BLE001 -- eager is always available
             sys.stderr.write("bench.py: CUDA graph capture failed (%s); running eagerly\n" % (e,))
-            self.graph = self.static = None
+            self.graph = self.graphs = self.static = None
 
-    def step(self, d=None):
+    def step(self, d=None, copy_in=None, copy_out=None):
         d = self.d if d is None else d
         # anchor targets: launch the label kernel first (own stream), queue the rest of the step,
         # then do the host-side subsampling while the GPU works through the queue
         pending = self.anchor_target.begin((d["src_prob"], d["src_gt"], d["src_im_info"], self.num_boxes))
-        if self.graph is not None and d is self.d:
-            self.graph.replay()
-            results = dict(self.static)
-        else:
-            results = self.device_part(d)
+        results = self.device_part(d, copy_in, copy_out)
         results["anchor_targets"] = self.anchor_target.finish(pending)
         return results
 
     def step_e2e(self):
         """Same step through host buffers: H2D of the inputs from pinned memory into the static
-        device buffers, the step, D2H of the results into pinned host buffers."""
-        for k, v in self.host.items():
-            self.d[k].detach().copy_(v, non_blocking=True)
-        r = self.step()
-        outs = []
-        for dom in ("src", "tgt"):
-            rois, gfeat, _, losses, _, _ = r[dom]
-            outs += [rois, gfeat, losses]
-        outs.append(r["anchor_targets"][0])
-        if self.host_out is None:
-            self.host_out = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
-        for h, o in zip(self.host_out, outs):
-            h.copy_(o, non_blocking=True)
+        device buffers, the step, D2H of the results into pinned host buffers; each domain's
+        copies ride on that domain's stream."""
+        d = self.d
+
+        def copy_in(dom):
+            for k, v in self.host.items():
+                if k.startswith(dom) and k not in ("src_gt", "src_im_info"):
+                    d[k].detach().copy_(v, non_blocking=True)
+
+        def copy_out(dom, results):
+            rois, gfeat, _, losses, _, _ = results[dom]
+            outs = [rois, gfeat, losses]
+            if self.host_out is None:
+                self.host_out = {}
+            if dom not in self.host_out:
+                self.host_out[dom] = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
+            for h, o in zip(self.host_out[dom], outs):
+                h.copy_(o, non_blocking=True)
+
+        d["src_gt"].copy_(self.host["src_gt"], non_blocking=True)  # the anchor-target layer reads these
+        d["src_im_info"].copy_(self.host["src_im_info"], non_blocking=True)
+        d["src_prob"].detach().copy_(self.host["src_prob"], non_blocking=True)
+        r = self.step(None, copy_in, copy_out)
+        at = r["anchor_targets"]
+        if "at" not in self.host_out:
+            self.host_out["at"] = torch.empty(at[0].shape, dtype=at[0].dtype).pin_memory()
+        self.host_out["at"].copy_(at[0], non_blocking=True)
         torch.cuda.current_stream(self.dev).synchronize()
         return self.host_out
 
@@ -354,9 +392,11 @@ def run_tlod(args):
     # per-kernel device time (CUDA events on the launch stream, inside the library)
     _lib.profile_reset()
     _lib.profile(True)
+    graphs, step.graphs = step.graphs, None  # eager: the library brackets each launch with events
     for _ in range(max(5, min(args.steps, 20))):
         flush.zero_()
-        step.anchor_part(step.d, step.device_part(step.d))  # eager: the library brackets each launch
+        step.anchor_part(step.d, step.device_part(step.d))
+    step.graphs = graphs
     torch.cuda.synchronize()
     prof = _lib.profile_read()
     _lib.profile(False)
