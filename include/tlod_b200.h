@@ -317,6 +317,29 @@ int tlod_da_loss_backward(const float* img_score, const float* ins_prob, const f
                           float* grad_ins_prob, int batch, int height, int width, int num_ins,
                           void* stream);
 
+/* ------------------------------------------------------------------------ */
+/* RPN head losses                                         */
+/*   lib/model/rpn/rpn.py:90-108 (keep = label != -1, index_select,           */
+/*   cross_entropy) and _smooth_l1_loss, lib/model/utils/net_utils.py:72-86   */
+/* ------------------------------------------------------------------------ */
+/* cls_score (batch, 2A, H, W) logits (bg = channels [0, A), fg = [A, 2A)); labels
+ * (batch, 1, A*H, W) fp32 in {-1, 0, 1} (the anchor-target layer's output); bbox_pred /
+ * bbox_targets / inside_w / outside_w (batch, 4A, H, W).
+ * losses_out[4] = { cross-entropy (mean over labels != -1), smooth-L1 (sum / batch),
+ * number of kept anchors, number of foreground anchors }.  Deterministic (fixed order). */
+size_t tlod_rpn_loss_workspace_bytes(void);
+int tlod_rpn_loss_forward(const float* cls_score, const float* labels, const float* bbox_pred,
+                          const float* bbox_targets, const float* inside_w, const float* outside_w,
+                          float* losses_out, int batch, int num_anchors, int height, int width,
+                          float sigma, void* workspace, size_t workspace_bytes, void* stream);
+/* Gradients of up[0]*loss_cls + up[1]*loss_box (upstream: 2 floats on the DEVICE or NULL = 1, 1)
+ * w.r.t. cls_score and bbox_pred, given losses_out of the forward call. */
+int tlod_rpn_loss_backward(const float* cls_score, const float* labels, const float* bbox_pred,
+                           const float* bbox_targets, const float* inside_w, const float* outside_w,
+                           const float* losses_out, const float* upstream, float* grad_cls_score,
+                           float* grad_bbox_pred, int batch, int num_anchors, int height, int width,
+                           float sigma, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -115,6 +115,30 @@ def grad_reverse(x, alpha=0.1, row_weight=None):
     return GradReverse.apply(x, alpha, row_weight)
 
 
+class RPNLossFunction(Function):
+    """(rpn_cls_score (B,2A,H,W), rpn_bbox_pred (B,4A,H,W), labels, targets, inside_w, outside_w) ->
+    (rpn_loss_cls, rpn_loss_box): lib/model/rpn/rpn.py:90-108 as one launch each way."""
+
+    @staticmethod
+    def forward(ctx, cls_score, bbox_pred, labels, bbox_targets, inside_w, outside_w, sigma=3.0):
+        losses = F.rpn_loss_forward(cls_score, labels, bbox_pred, bbox_targets, inside_w, outside_w, sigma)
+        ctx.save_for_backward(cls_score, bbox_pred, labels, bbox_targets, inside_w, outside_w, losses)
+        ctx.sigma = float(sigma)
+        return losses[0], losses[1]
+
+    @staticmethod
+    def backward(ctx, g_cls, g_box):
+        cls_score, bbox_pred, labels, targets, inside_w, outside_w, losses = ctx.saved_tensors
+        up = torch.stack([g_cls.reshape(()), g_box.reshape(())]).float()
+        gs, gp = F.rpn_loss_backward(cls_score, labels, bbox_pred, targets, inside_w, outside_w, losses, up,
+                                     ctx.sigma)
+        return gs.view_as(cls_score), gp.view_as(bbox_pred), None, None, None, None, None
+
+
+def rpn_losses(cls_score, bbox_pred, labels, bbox_targets, inside_w, outside_w, sigma=3.0):
+    return RPNLossFunction.apply(cls_score, bbox_pred, labels, bbox_targets, inside_w, outside_w, sigma)
+
+
 class DALossFunction(Function):
     """(img_score (B,2,H,W), ins_prob (R,1)) -> (img_loss, ins_loss, cst_loss) for one domain,
     lib/DAF/faster_rcnn.py:181-220.  One launch forward, one backward, no label tensors."""

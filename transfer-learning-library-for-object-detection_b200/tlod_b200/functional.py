@@ -422,6 +422,43 @@ def proposal_targets(all_rois, gt_boxes, assignment, labels, keep, fg_count, mea
 
 
 # ---------------------------------------------------------------------------
+# RPN head losses
+# ---------------------------------------------------------------------------
+def rpn_loss_forward(cls_score, labels, bbox_pred, bbox_targets, inside_w, outside_w, sigma: float = 3.0):
+    """-> (4,) device tensor [loss_cls, loss_box, kept anchors, foreground anchors]."""
+    _require_cuda(cls_score, labels, bbox_pred, bbox_targets, inside_w, outside_w)
+    ts = [_f32(t) for t in (cls_score, labels, bbox_pred, bbox_targets, inside_w, outside_w)]
+    B, A2, H, W = ts[0].shape
+    A = A2 // 2
+    if ts[1].numel() != B * A * H * W or any(t.numel() != B * 4 * A * H * W for t in ts[2:]):
+        raise ValueError("inconsistent RPN loss shapes")
+    dev = ts[0].device
+    out = torch.empty((4,), dtype=torch.float32, device=dev)
+    ws = _workspace(dev, lib.tlod_rpn_loss_workspace_bytes(), "rpn_loss")
+    with torch.cuda.device(dev):
+        check(lib.tlod_rpn_loss_forward(*[t.data_ptr() for t in ts], out.data_ptr(), B, A, H, W, float(sigma),
+                                        ws.data_ptr(), ws.numel(), _stream(dev)), "tlod_rpn_loss_forward")
+    return out
+
+
+def rpn_loss_backward(cls_score, labels, bbox_pred, bbox_targets, inside_w, outside_w, losses, upstream=None,
+                      sigma: float = 3.0):
+    _require_cuda(cls_score, labels, bbox_pred, bbox_targets, inside_w, outside_w, losses, upstream)
+    ts = [_f32(t) for t in (cls_score, labels, bbox_pred, bbox_targets, inside_w, outside_w)]
+    B, A2, H, W = ts[0].shape
+    A = A2 // 2
+    g_score = torch.empty_like(ts[0])
+    g_pred = torch.empty_like(ts[2])
+    up = None if upstream is None else _f32(upstream)
+    dev = ts[0].device
+    with torch.cuda.device(dev):
+        check(lib.tlod_rpn_loss_backward(*[t.data_ptr() for t in ts], losses.data_ptr(), _ptr(up),
+                                         g_score.data_ptr(), g_pred.data_ptr(), B, A, H, W, float(sigma),
+                                         _stream(dev)), "tlod_rpn_loss_backward")
+    return g_score, g_pred
+
+
+# ---------------------------------------------------------------------------
 # GRL + DA losses
 # ---------------------------------------------------------------------------
 def grl_backward(grad, alpha: float, row_weight=None):
