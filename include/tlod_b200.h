@@ -340,6 +340,23 @@ int tlod_rpn_loss_backward(const float* cls_score, const float* labels, const fl
                            float* grad_bbox_pred, int batch, int num_anchors, int height, int width,
                            float sigma, void* stream);
 
+/* ------------------------------------------------------------------------ */
+/* MAF / PT-MAF scale-reduce rearrangement and label layers */
+/*   lib/MAF/drm.py:21-42 (chunk / reshape / cat loops = space-to-depth),     */
+/*   lib/DAF/LabelResizeLayer.py:42-58 (instance labels in blocks of 256)     */
+/* ------------------------------------------------------------------------ */
+/* in (batch, C, H, W) -> out (batch, C*s*s, H/s, W/s):
+ * out[b, c*s*s + dy*s + dx, i, j] = in[b, c, i*s + dy, j*s + dx]; the border beyond
+ * s*floor(H/s), s*floor(W/s) is dropped (backward writes zeros there). */
+int tlod_space_to_depth_forward(const float* in, float* out, int batch, int channels, int height,
+                                int width, int scale, void* stream);
+int tlod_space_to_depth_backward(const float* grad_out, float* grad_in, int batch, int channels,
+                                 int height, int width, int scale, void* stream);
+/* out[r] = domain_labels[r / minibatch] for r < images * minibatch, else `fill`
+ * (DAF: np.ones -> 1, MAF / ATF: np.zeros -> 0); domain_labels (images) on the device. */
+int tlod_instance_labels(const float* domain_labels, float* out, int rows, int images, int minibatch,
+                         float fill, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

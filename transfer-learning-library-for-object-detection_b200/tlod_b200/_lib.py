@@ -62,6 +62,9 @@ SIGNATURES = {
     "tlod_rpn_loss_workspace_bytes": (c_size_t, []),
     "tlod_rpn_loss_forward": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_float, P, c_size_t, P]),
     "tlod_rpn_loss_backward": (c_int, [P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_float, P]),
+    "tlod_space_to_depth_forward": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "tlod_space_to_depth_backward": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "tlod_instance_labels": (c_int, [P, P, c_int, c_int, c_int, c_float, P]),
     "tlod_grl_backward": (c_int, [P, P, c_float, c_longlong, P]),
     "tlod_grl_backward_weighted": (c_int, [P, P, P, c_float, c_int, c_int, P]),
     "tlod_da_loss_workspace_bytes": (c_size_t, []),

@@ -139,6 +139,24 @@ def rpn_losses(cls_score, bbox_pred, labels, bbox_targets, inside_w, outside_w, 
     return RPNLossFunction.apply(cls_score, bbox_pred, labels, bbox_targets, inside_w, outside_w, sigma)
 
 
+class SpaceToDepthFunction(Function):
+    """The rearrangement of DRM.forward (lib/MAF/drm.py:21-42) as one launch each way."""
+
+    @staticmethod
+    def forward(ctx, x, scale):
+        ctx.input_size = tuple(x.shape)
+        ctx.scale = int(scale)
+        return F.space_to_depth_forward(x, ctx.scale)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return F.space_to_depth_backward(grad_output, ctx.input_size, ctx.scale), None
+
+
+def space_to_depth(x, scale):
+    return SpaceToDepthFunction.apply(x, scale)
+
+
 class DALossFunction(Function):
     """(img_score (B,2,H,W), ins_prob (R,1)) -> (img_loss, ins_loss, cst_loss) for one domain,
     lib/DAF/faster_rcnn.py:181-220.  One launch forward, one backward, no label tensors."""

@@ -459,6 +459,44 @@ def rpn_loss_backward(cls_score, labels, bbox_pred, bbox_targets, inside_w, outs
 
 
 # ---------------------------------------------------------------------------
+# MAF scale-reduce rearrangement, label layers
+# ---------------------------------------------------------------------------
+def space_to_depth_forward(x, scale: int):
+    _require_cuda(x)
+    x = _f32(x)
+    B, C, H, W = x.shape
+    s = int(scale)
+    out = torch.empty((B, C * s * s, H // s, W // s), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.tlod_space_to_depth_forward(x.data_ptr(), out.data_ptr(), B, C, H, W, s, _stream(x.device)),
+              "tlod_space_to_depth_forward")
+    return out
+
+
+def space_to_depth_backward(grad_out, input_size, scale: int):
+    _require_cuda(grad_out)
+    g = _f32(grad_out)
+    B, C, H, W = [int(v) for v in input_size]
+    out = torch.empty((B, C, H, W), dtype=torch.float32, device=g.device)
+    with torch.cuda.device(g.device):
+        check(lib.tlod_space_to_depth_backward(g.data_ptr(), out.data_ptr(), B, C, H, W, int(scale),
+                                               _stream(g.device)), "tlod_space_to_depth_backward")
+    return out
+
+
+def instance_labels(domain_labels, rows: int, minibatch: int = 256, fill: float = 1.0):
+    """(images,) domain labels on the device -> (rows, 1): LabelResizeLayer.py:42-58 without the
+    two .cpu() copies."""
+    _require_cuda(domain_labels)
+    d = _f32(domain_labels).view(-1)
+    out = torch.empty((int(rows), 1), dtype=torch.float32, device=d.device)
+    with torch.cuda.device(d.device):
+        check(lib.tlod_instance_labels(d.data_ptr(), out.data_ptr(), int(rows), d.numel(), int(minibatch),
+                                       float(fill), _stream(d.device)), "tlod_instance_labels")
+    return out
+
+
+# ---------------------------------------------------------------------------
 # GRL + DA losses
 # ---------------------------------------------------------------------------
 def grl_backward(grad, alpha: float, row_weight=None):
