@@ -1,0 +1,343 @@
+// RoIAlign backward for sm_100a: row-resident, no global atomics, no memset.
+//
+// Reference semantics: lib/model/roi_align/src/roi_align_kernel.cu:94-143 (4 fp32 atomicAdd
+// per output element, 537 M at BASELINE cfg3); glue roi_align_cuda.c:42-76.
+//
+// One warp (= one CTA) owns one row of the gradient map for 32 channels:
+// (image b, plane row y, channels 32g .. 32g+31).  Lane = channel, so a cell is only ever
+// touched by one thread: the scatter is plain load-add-store on shared memory in a fixed order
+// (bitwise reproducible), and the finished row is written to HBM once, coalesced.
+//
+// The plan (roi_align.cu) holds, per (image, plane row), the list of gradient rows (RoI n,
+// output row ph, row weight) that feed it.  The warp walks its list:
+//   * lane 0 fetches the 32-byte gradient rows of the warp's 32 channels (256 B apart in HBM)
+//     with one TMA tile copy (tensor map over (R, C, AH, 8), box 8 x 1 x 32 x 1, 32-byte
+//     swizzle) into a private ring of stages, and the RoI's column chain (BwdCols, 208 B) with
+//     a bulk copy on the same mbarrier when the RoI changes; the tiles of the items further
+//     ahead are pulled into L2 with TMA prefetches;
+//   * every lane reads its channel's row with two conflict-free LDS.128 and adds weight * row
+//     into 8 registers -- all output rows of a RoI have the same column structure, so the rows
+//     that feed this plane row are summed first;
+//   * when the RoI changes, the column chain turns the 8 sums into <= 16 distinct cells, which
+//     are added to the row: 16 loads, 16 adds, 16 stores, no predicates (sites that are not
+//     emitted point at a dump cell behind the row).
+// Warps are independent: no block-wide synchronisation anywhere, and the grid (B * H * C/32
+// one-warp CTAs) is balanced by the hardware scheduler.
+#include <cuda.h>
+
+#include "roi_align_plan.cuh"
+
+namespace tlod {
+
+constexpr int RW_STAGES = 4;
+constexpr int RW_TILE_BYTES = 32 * 32;  // 32 channels x one 32-byte gradient row
+constexpr int RW_STAGE_BYTES = RW_TILE_BYTES + 256;  // + BwdCols (208), padded: keeps the swizzle phase
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  unsigned done = 0;
+  // bounded: a lost TMA transaction must fault the launch, not hang the device
+  for (unsigned spins = 0; !done; ++spins) {
+    if (spins > (1u << 24)) __trap();
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ bool elect_one() {
+  unsigned pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void bulk_load(unsigned smem_dst, const void* gsrc, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_dst),
+               "l"(gsrc), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(unsigned smem_dst, const void* tmap, unsigned bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_dst),
+      "l"((unsigned long long)tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_4d(const void* tmap, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(
+                   (unsigned long long)tmap),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(unsigned addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float4 lds_v4(unsigned addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+// column state of the current RoI, for this lane's row
+struct RowCols {
+  float cw0[8], cw1[8], ms[8], mh[8];
+  unsigned sa[16];  // shared-window address of site j in this lane's row (or of its dump cell)
+  int all_jump;
+};
+
+// all lanes read the same 208 bytes (broadcast)
+__device__ __forceinline__ void rw_load_cols(RowCols& s, unsigned meta, unsigned row_addr) {
+  float4 v[13];
+#pragma unroll
+  for (int i = 0; i < 13; ++i) v[i] = lds_v4(meta + 16u * i);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    s.cw0[4 * i] = v[i].x; s.cw0[4 * i + 1] = v[i].y; s.cw0[4 * i + 2] = v[i].z; s.cw0[4 * i + 3] = v[i].w;
+    s.cw1[4 * i] = v[2 + i].x; s.cw1[4 * i + 1] = v[2 + i].y; s.cw1[4 * i + 2] = v[2 + i].z; s.cw1[4 * i + 3] = v[2 + i].w;
+    s.ms[4 * i] = v[4 + i].x; s.ms[4 * i + 1] = v[4 + i].y; s.ms[4 * i + 2] = v[4 + i].z; s.ms[4 * i + 3] = v[4 + i].w;
+    s.mh[4 * i] = v[6 + i].x; s.mh[4 * i + 1] = v[6 + i].y; s.mh[4 * i + 2] = v[6 + i].z; s.mh[4 * i + 3] = v[6 + i].w;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    s.sa[4 * i] = row_addr + (unsigned)__float_as_int(v[8 + i].x);
+    s.sa[4 * i + 1] = row_addr + (unsigned)__float_as_int(v[8 + i].y);
+    s.sa[4 * i + 2] = row_addr + (unsigned)__float_as_int(v[8 + i].z);
+    s.sa[4 * i + 3] = row_addr + (unsigned)__float_as_int(v[8 + i].w);
+  }
+  s.all_jump = __float_as_int(v[12].x);
+}
+
+// The RoI's summed gradient rows m -> values of the 16 column sites (the chain of BwdCols) ->
+// added to the row.  The loads of the old values are issued first, so that the serial chain runs
+// under their latency; all 16 cells are distinct (or dump cells), so the order is free.
+__device__ __forceinline__ void rw_flush(const RowCols& s, const float (&m)[8]) {
+  float o[16], e[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) o[j] = lds_f32(s.sa[j]);
+  if (s.all_jump) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      sts_f32(s.sa[2 * t], fmaf(m[t], s.cw0[t], o[2 * t]));
+      sts_f32(s.sa[2 * t + 1], fmaf(m[t], s.cw1[t], o[2 * t + 1]));
+    }
+    return;
+  } else {
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      if (t > 0) { e[2 * (t - 1)] = a0; e[2 * (t - 1) + 1] = a1; }
+      const float na0 = fmaf(s.ms[t], a0, fmaf(s.mh[t], a1, m[t] * s.cw0[t]));
+      a1 = fmaf(s.ms[t], a1, m[t] * s.cw1[t]);
+      a0 = na0;
+    }
+    e[14] = a0; e[15] = a1;
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) sts_f32(s.sa[j], o[j] + e[j]);
+}
+
+__global__ void __launch_bounds__(32, 16)
+    roi_align_bwd_rows_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ bottom_grad,
+                              PlanPtrs pl, int B, int C, int H, int W, int Ws) {
+  extern __shared__ __align__(1024) unsigned char smem_rw[];
+  // [stages][row: 32 channels x Ws floats][full barriers]
+  const unsigned stages = smem_u32(smem_rw);
+  float* row = reinterpret_cast<float*>(smem_rw + RW_STAGES * RW_STAGE_BYTES);
+  const unsigned bars = smem_u32(row + 32 * Ws);
+  const int lane = lane_id();
+  const int y = blockIdx.x % H;
+  const int rest = blockIdx.x / H;
+  const int groups = C / 32;
+  const int grp = rest % groups, img = rest / groups;
+  const int c0 = grp * 32;
+  const unsigned row_addr = smem_u32(row + lane * Ws);
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < RW_STAGES; ++s) mbar_init(bars + 8u * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = lane; i < 32 * Ws; i += 32) row[i] = 0.f;
+  __syncwarp();
+
+  const int bin = img * H + y;
+  const int cnt = __ldg(pl.rowcnt + bin);
+  const RowItem* __restrict__ items = pl.items + __ldg(pl.rowptr + bin);
+
+  // lane's 32-byte row inside a tile, 16-byte halves swapped by the 32-byte swizzle
+  const unsigned g_lo = (unsigned)(lane * 32 + (((lane >> 2) & 1) << 4));
+  const unsigned g_hi = g_lo ^ 16u;
+
+  // The issue stream reads the list sequentially: 32 entries per coalesced load, one chunk ahead,
+  // handed out by shuffles (no global-memory latency on the per-item path).
+  const int2* __restrict__ items2 = reinterpret_cast<const int2*>(items);
+  int2 chunk = lane < cnt ? __ldg(items2 + lane) : make_int2(0, 0);
+  int2 chunk_next = 32 + lane < cnt ? __ldg(items2 + 32 + lane) : make_int2(0, 0);
+  int issue_prev = -1;  // RoI of the item issued last (its BwdCols travel with the first item of a RoI)
+  int en[RW_STAGES];    // RoI of the item in stage s
+  float ew[RW_STAGES];  // its row weight
+  // all lanes run this (warp-uniform); one elected lane issues the asynchronous copies
+  auto issue = [&](int j, int s) {
+    const int x = __shfl_sync(0xffffffffu, chunk.x, j & 31);
+    const int n = x >> 4, ph = x & 15;
+    en[s] = n;
+    ew[s] = __int_as_float(__shfl_sync(0xffffffffu, chunk.y, j & 31));
+    const unsigned bar = bars + 8u * s, stg = stages + (unsigned)(s * RW_STAGE_BYTES);
+    const bool fresh = n != issue_prev;
+    if (elect_one()) {
+      mbar_arrive_expect_tx(bar, RW_TILE_BYTES + (fresh ? (unsigned)sizeof(BwdCols) : 0u));
+      tma_load_4d(stg, &tmap, bar, 0, ph, c0, n);
+      if (fresh) bulk_load(stg + RW_TILE_BYTES, pl.bwdx + n, (unsigned)sizeof(BwdCols), bar);
+    }
+    issue_prev = n;
+  };
+
+#pragma unroll
+  for (int s = 0; s < RW_STAGES; ++s)
+    if (s < cnt) issue(s, s);
+
+  // column state of the current RoI; before the first one every site is the dump cell
+  RowCols st;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) { st.cw0[t] = 0.f; st.cw1[t] = 0.f; st.ms[t] = 0.f; st.mh[t] = 0.f; }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) st.sa[j] = row_addr + 4u * (unsigned)W;
+  st.all_jump = 1;
+  int cur = -1;
+  float m[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) m[t] = 0.f;
+
+  for (int base = 0; base < cnt; base += RW_STAGES) {
+    const unsigned parity = (unsigned)(base / RW_STAGES) & 1u;
+    if (((base + RW_STAGES) & 31) == 0) {  // the issue stream enters the next chunk (32 % RW_STAGES == 0)
+      chunk = chunk_next;
+      const int k = base + RW_STAGES + 32 + lane;
+      chunk_next = k < cnt ? __ldg(items2 + k) : make_int2(0, 0);
+    }
+#pragma unroll
+    for (int s = 0; s < RW_STAGES; ++s) {
+      const int i = base + s;
+      if (i < cnt) {
+        const unsigned stg = stages + (unsigned)(s * RW_STAGE_BYTES);
+        mbar_wait(bars + 8u * s, parity);
+        const int n = en[s];
+        const float w = ew[s];
+        if (n != cur) {
+          rw_flush(st, m);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) m[t] = 0.f;
+          rw_load_cols(st, stg + RW_TILE_BYTES, row_addr);
+          cur = n;
+        }
+        const float4 ga = lds_v4(stg + g_lo), gb = lds_v4(stg + g_hi);
+        m[0] = fmaf(w, ga.x, m[0]); m[1] = fmaf(w, ga.y, m[1]); m[2] = fmaf(w, ga.z, m[2]); m[3] = fmaf(w, ga.w, m[3]);
+        m[4] = fmaf(w, gb.x, m[4]); m[5] = fmaf(w, gb.y, m[5]); m[6] = fmaf(w, gb.z, m[6]); m[7] = fmaf(w, gb.w, m[7]);
+        // the stage has been read (the sums above depend on it): refill it
+        __syncwarp();
+        if (i + RW_STAGES < cnt) issue(i + RW_STAGES, s);
+      }
+    }
+  }
+  rw_flush(st, m);
+  __syncwarp();
+
+  // ---- write the row: 32 channels, lanes along the cells ----
+  float* out = bottom_grad + (((size_t)img * C + c0) * H + y) * W;
+  const size_t plane = (size_t)H * W;
+  for (int ch = 0; ch < 32; ++ch)
+    for (int x = lane; x < W; x += 32) out[ch * plane + x] = row[ch * Ws + x];
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &p, 12000, cudaEnableDefault, &q) !=
+            cudaSuccess || q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+// (R, C, AH, 8) fp32 gradient tensor; box = one 8-wide row of 32 consecutive channels
+static bool make_grad_tmap(CUtensorMap* map, const float* top_grad, int R, int C, int AH) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[4] = {8, (cuuint64_t)AH, (cuuint64_t)C, (cuuint64_t)R};
+  const cuuint64_t strides[3] = {32, (cuuint64_t)AH * 32, (cuuint64_t)C * AH * 32};
+  const cuuint32_t box[4] = {8, 1, 32, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(top_grad), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace tlod
+
+using namespace tlod;
+
+extern "C" int tlod_roi_align_backward(const float* top_grad, const float* rois, float* bottom_grad,
+                                       int batch, int channels, int height, int width,
+                                       int num_rois, int aligned_h, int aligned_w,
+                                       float spatial_scale, const void* plan, size_t plan_bytes,
+                                       void* stream) {
+  int rc = roi_align_check_common(top_grad, rois, bottom_grad, batch, channels, height, width, num_rois,
+                                  aligned_h, aligned_w);
+  if (rc != TLOD_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t grad_bytes = (size_t)batch * channels * height * width * sizeof(float);
+  if (num_rois == 0) return (int)cudaMemsetAsync(bottom_grad, 0, grad_bytes, st);
+  if (plan && (plan_bytes < tlod_roi_align_plan_bytes(batch, num_rois) || ((uintptr_t)plan & 255)))
+    return TLOD_ERR_WORKSPACE;
+  const bool planned = plan != nullptr && plan_supported(batch, height, width, aligned_h, aligned_w);
+
+  // row-resident path: AW == 8 (one 32-byte gradient row per item), C % 32 == 0, row lists in the plan
+  if (planned && plan_has_row_lists(batch, height) && channels % 32 == 0 && aligned_w == 8 &&
+      ((uintptr_t)top_grad & 15) == 0) {
+    const int Ws = (width + 1) | 1;  // + dump cell; odd stride: lane = channel is conflict free
+    const size_t smem = (size_t)RW_STAGES * RW_STAGE_BYTES + (size_t)32 * Ws * sizeof(float) + RW_STAGES * 8;
+    const long long grid = (long long)batch * height * (channels / 32);
+    CUtensorMap tmap;
+    if (grid <= 2147483647LL && smem <= (size_t)device_info().max_smem_optin &&
+        make_grad_tmap(&tmap, top_grad, num_rois, channels, aligned_h)) {
+      cudaError_t e = cudaFuncSetAttribute(roi_align_bwd_rows_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      const PlanPtrs pl = plan_ptrs(const_cast<void*>(plan), batch, num_rois);
+      {
+        LaunchScope scope("roi_align_bwd_rows_kernel", st);
+        roi_align_bwd_rows_kernel<<<(int)grid, 32, smem, st>>>(tmap, bottom_grad, pl, batch, channels, height,
+                                                              width, Ws);
+      }
+      return last_launch_status();
+    }
+  }
+  cudaError_t e = cudaMemsetAsync(bottom_grad, 0, grad_bytes, st);
+  if (e != cudaSuccess) return (int)e;
+  return roi_align_generic_launch(true, top_grad, rois, bottom_grad, batch, channels, height, width, num_rois,
+                                  aligned_h, aligned_w, spatial_scale, st);
+}
