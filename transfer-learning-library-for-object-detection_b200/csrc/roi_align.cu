@@ -227,15 +227,18 @@ __global__ void __launch_bounds__(PL_THREADS)
     BwdCols* bc = pl.bwdx + n;
     // lane t (0..7) holds ex of transition t; sites belong to transitions 1..8
     const int ex_next = __shfl_down_sync(0xffffffffu, my_ex, 1);  // lane t: ex[t + 1]
+    const int my_x = __shfl_sync(0xffffffffu, t.off, 16 + (lane & 7));
     if (lane < 8) {
       bc->cw0[lane] = my_cw0; bc->cw1[lane] = my_cw1; bc->ms[lane] = my_ms; bc->mh[lane] = my_mh;
+      bc->xoff[lane] = all_jump ? my_x * 4 : W * 4;
       const int t = lane + 1;
       const int ex = (t == 8) ? ex8 : ex_next;
       bc->soff[2 * lane] = ((en0 >> t) & 1u) ? ex * 4 : W * 4;  // W * 4: the dump cell
       bc->soff[2 * lane + 1] = ((en1 >> t) & 1u) ? (ex + 1) * 4 : W * 4;
-    } else if (lane == 8) {
-      bc->all_jump = all_jump;
     }
+    if (lane == 0) pl.jump[n] = (unsigned char)all_jump;
+  } else if (lane == 0) {
+    pl.jump[n] = 0;
   }
 }
 
@@ -288,7 +291,7 @@ __global__ void __launch_bounds__(PL_THREADS)
       both &= both - 1u;
       const float4 t = __ldg(pl.tabs + (size_t)n * 32 + ph);
       RowItem it;
-      it.roi_ph = (n << 4) | ph;
+      it.roi_ph = (n << 5) | ((int)__ldg(pl.jump + n) << 4) | ph;
       it.weight = ((hit0 >> ph) & 1u) ? t.y : t.z;
       *o++ = it;
     }

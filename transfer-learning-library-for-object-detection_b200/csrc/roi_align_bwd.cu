@@ -13,8 +13,7 @@
 //   * lane 0 fetches the 32-byte gradient rows of the warp's 32 channels (256 B apart in HBM)
 //     with one TMA tile copy (tensor map over (R, C, AH, 8), box 8 x 1 x 32 x 1, 32-byte
 //     swizzle) into a private ring of stages, and the RoI's column chain (BwdCols, 208 B) with
-//     a bulk copy on the same mbarrier when the RoI changes; the tiles of the items further
-//     ahead are pulled into L2 with TMA prefetches;
+//     a bulk copy on the same mbarrier when the RoI changes;
 //   * every lane reads its channel's row with two conflict-free LDS.128 and adds weight * row
 //     into 8 registers -- all output rows of a RoI have the same column structure, so the rows
 //     that feed this plane row are summed first;
@@ -98,57 +97,65 @@ __device__ __forceinline__ float4 lds_v4(unsigned addr) {
 // column state of the current RoI, for this lane's row
 struct RowCols {
   float cw0[8], cw1[8], ms[8], mh[8];
-  unsigned sa[16];  // shared-window address of site j in this lane's row (or of its dump cell)
-  int all_jump;
+  unsigned sa[16];  // shared-window address of site j in this lane's row (or of its dump cell);
+                    // all-jump RoIs: sa[t] = first cell of sample t, t < 8
 };
 
-// all lanes read the same 208 bytes (broadcast)
-__device__ __forceinline__ void rw_load_cols(RowCols& s, unsigned meta, unsigned row_addr) {
-  float4 v[13];
-#pragma unroll
-  for (int i = 0; i < 13; ++i) v[i] = lds_v4(meta + 16u * i);
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    s.cw0[4 * i] = v[i].x; s.cw0[4 * i + 1] = v[i].y; s.cw0[4 * i + 2] = v[i].z; s.cw0[4 * i + 3] = v[i].w;
-    s.cw1[4 * i] = v[2 + i].x; s.cw1[4 * i + 1] = v[2 + i].y; s.cw1[4 * i + 2] = v[2 + i].z; s.cw1[4 * i + 3] = v[2 + i].w;
-    s.ms[4 * i] = v[4 + i].x; s.ms[4 * i + 1] = v[4 + i].y; s.ms[4 * i + 2] = v[4 + i].z; s.ms[4 * i + 3] = v[4 + i].w;
-    s.mh[4 * i] = v[6 + i].x; s.mh[4 * i + 1] = v[6 + i].y; s.mh[4 * i + 2] = v[6 + i].z; s.mh[4 * i + 3] = v[6 + i].w;
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    s.sa[4 * i] = row_addr + (unsigned)__float_as_int(v[8 + i].x);
-    s.sa[4 * i + 1] = row_addr + (unsigned)__float_as_int(v[8 + i].y);
-    s.sa[4 * i + 2] = row_addr + (unsigned)__float_as_int(v[8 + i].z);
-    s.sa[4 * i + 3] = row_addr + (unsigned)__float_as_int(v[8 + i].w);
-  }
-  s.all_jump = __float_as_int(v[12].x);
+__device__ __forceinline__ void rw_unpack(float (&d)[8], const float4 a, const float4 b) {
+  d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+}
+__device__ __forceinline__ void rw_unpack_addr(unsigned* d, const float4 a, unsigned row_addr) {
+  d[0] = row_addr + (unsigned)__float_as_int(a.x); d[1] = row_addr + (unsigned)__float_as_int(a.y);
+  d[2] = row_addr + (unsigned)__float_as_int(a.z); d[3] = row_addr + (unsigned)__float_as_int(a.w);
 }
 
-// The RoI's summed gradient rows m -> values of the 16 column sites (the chain of BwdCols) ->
-// added to the row.  The loads of the old values are issued first, so that the serial chain runs
-// under their latency; all 16 cells are distinct (or dump cells), so the order is free.
-__device__ __forceinline__ void rw_flush(const RowCols& s, const float (&m)[8]) {
+// all lanes read the same bytes (broadcast).  JUMP: the 96-byte head of BwdCols; else all of it.
+template <bool JUMP>
+__device__ __forceinline__ void rw_load_cols(RowCols& s, unsigned meta, unsigned row_addr) {
+  rw_unpack(s.cw0, lds_v4(meta), lds_v4(meta + 16));
+  rw_unpack(s.cw1, lds_v4(meta + 32), lds_v4(meta + 48));
+  if (JUMP) {
+    rw_unpack_addr(s.sa, lds_v4(meta + 64), row_addr);
+    rw_unpack_addr(s.sa + 4, lds_v4(meta + 80), row_addr);
+  } else {
+    rw_unpack(s.ms, lds_v4(meta + 96), lds_v4(meta + 112));
+    rw_unpack(s.mh, lds_v4(meta + 128), lds_v4(meta + 144));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) rw_unpack_addr(s.sa + 4 * i, lds_v4(meta + 160 + 16 * i), row_addr);
+  }
+}
+
+// The RoI's summed gradient rows m -> values of the 16 column sites -> added to the row.
+// All-jump RoIs: sample t owns cells (x_t, x_t + 1) alone.
+__device__ __forceinline__ void rw_flush_jump(const RowCols& s, const float (&m)[8]) {
+  float o0[8], o1[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    o0[t] = lds_f32(s.sa[t]);
+    o1[t] = lds_f32(s.sa[t] + 4u);
+  }
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    sts_f32(s.sa[t], fmaf(m[t], s.cw0[t], o0[t]));
+    sts_f32(s.sa[t] + 4u, fmaf(m[t], s.cw1[t], o1[t]));
+  }
+}
+// General RoIs: the chain of BwdCols.  The loads of the old values are issued first, so that the
+// serial chain runs under their latency; all 16 cells are distinct (or dump cells), so the order
+// is free.
+__device__ __forceinline__ void rw_flush_chain(const RowCols& s, const float (&m)[8]) {
   float o[16], e[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) o[j] = lds_f32(s.sa[j]);
-  if (s.all_jump) {
+  float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      sts_f32(s.sa[2 * t], fmaf(m[t], s.cw0[t], o[2 * t]));
-      sts_f32(s.sa[2 * t + 1], fmaf(m[t], s.cw1[t], o[2 * t + 1]));
-    }
-    return;
-  } else {
-    float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      if (t > 0) { e[2 * (t - 1)] = a0; e[2 * (t - 1) + 1] = a1; }
-      const float na0 = fmaf(s.ms[t], a0, fmaf(s.mh[t], a1, m[t] * s.cw0[t]));
-      a1 = fmaf(s.ms[t], a1, m[t] * s.cw1[t]);
-      a0 = na0;
-    }
-    e[14] = a0; e[15] = a1;
+  for (int t = 0; t < 8; ++t) {
+    if (t > 0) { e[2 * (t - 1)] = a0; e[2 * (t - 1) + 1] = a1; }
+    const float na0 = fmaf(s.ms[t], a0, fmaf(s.mh[t], a1, m[t] * s.cw0[t]));
+    a1 = fmaf(s.ms[t], a1, m[t] * s.cw1[t]);
+    a0 = na0;
   }
+  e[14] = a0; e[15] = a1;
 #pragma unroll
   for (int j = 0; j < 16; ++j) sts_f32(s.sa[j], o[j] + e[j]);
 }
@@ -191,20 +198,20 @@ __global__ void __launch_bounds__(32, 16)
   int2 chunk = lane < cnt ? __ldg(items2 + lane) : make_int2(0, 0);
   int2 chunk_next = 32 + lane < cnt ? __ldg(items2 + 32 + lane) : make_int2(0, 0);
   int issue_prev = -1;  // RoI of the item issued last (its BwdCols travel with the first item of a RoI)
-  int en[RW_STAGES];    // RoI of the item in stage s
+  int en[RW_STAGES];    // (RoI << 1) | all_jump of the item in stage s
   float ew[RW_STAGES];  // its row weight
   // all lanes run this (warp-uniform); one elected lane issues the asynchronous copies
   auto issue = [&](int j, int s) {
     const int x = __shfl_sync(0xffffffffu, chunk.x, j & 31);
-    const int n = x >> 4, ph = x & 15;
+    const int n = x >> 4, ph = x & 15;  // n = (RoI << 1) | all_jump
     en[s] = n;
     ew[s] = __int_as_float(__shfl_sync(0xffffffffu, chunk.y, j & 31));
     const unsigned bar = bars + 8u * s, stg = stages + (unsigned)(s * RW_STAGE_BYTES);
-    const bool fresh = n != issue_prev;
+    const unsigned cols = n == issue_prev ? 0u : ((n & 1) ? BWDCOLS_JUMP_BYTES : (unsigned)sizeof(BwdCols));
     if (elect_one()) {
-      mbar_arrive_expect_tx(bar, RW_TILE_BYTES + (fresh ? (unsigned)sizeof(BwdCols) : 0u));
-      tma_load_4d(stg, &tmap, bar, 0, ph, c0, n);
-      if (fresh) bulk_load(stg + RW_TILE_BYTES, pl.bwdx + n, (unsigned)sizeof(BwdCols), bar);
+      mbar_arrive_expect_tx(bar, RW_TILE_BYTES + cols);
+      tma_load_4d(stg, &tmap, bar, 0, ph, c0, n >> 1);
+      if (cols) bulk_load(stg + RW_TILE_BYTES, pl.bwdx + (n >> 1), cols, bar);
     }
     issue_prev = n;
   };
@@ -219,8 +226,7 @@ __global__ void __launch_bounds__(32, 16)
   for (int t = 0; t < 8; ++t) { st.cw0[t] = 0.f; st.cw1[t] = 0.f; st.ms[t] = 0.f; st.mh[t] = 0.f; }
 #pragma unroll
   for (int j = 0; j < 16; ++j) st.sa[j] = row_addr + 4u * (unsigned)W;
-  st.all_jump = 1;
-  int cur = -1;
+  int cur = -1;  // never an item's key; odd: the first flush takes the all-jump path, into the dump cell
   float m[8];
 #pragma unroll
   for (int t = 0; t < 8; ++t) m[t] = 0.f;
@@ -240,14 +246,15 @@ __global__ void __launch_bounds__(32, 16)
         mbar_wait(bars + 8u * s, parity);
         const int n = en[s];
         const float w = ew[s];
+        const float4 ga = lds_v4(stg + g_lo), gb = lds_v4(stg + g_hi);
         if (n != cur) {
-          rw_flush(st, m);
+          if (cur & 1) rw_flush_jump(st, m); else rw_flush_chain(st, m);
 #pragma unroll
           for (int t = 0; t < 8; ++t) m[t] = 0.f;
-          rw_load_cols(st, stg + RW_TILE_BYTES, row_addr);
+          if (n & 1) rw_load_cols<true>(st, stg + RW_TILE_BYTES, row_addr);
+          else rw_load_cols<false>(st, stg + RW_TILE_BYTES, row_addr);
           cur = n;
         }
-        const float4 ga = lds_v4(stg + g_lo), gb = lds_v4(stg + g_hi);
         m[0] = fmaf(w, ga.x, m[0]); m[1] = fmaf(w, ga.y, m[1]); m[2] = fmaf(w, ga.z, m[2]); m[3] = fmaf(w, ga.w, m[3]);
         m[4] = fmaf(w, gb.x, m[4]); m[5] = fmaf(w, gb.y, m[5]); m[6] = fmaf(w, gb.z, m[6]); m[7] = fmaf(w, gb.w, m[7]);
         // the stage has been read (the sums above depend on it): refill it
@@ -256,7 +263,7 @@ __global__ void __launch_bounds__(32, 16)
       }
     }
   }
-  rw_flush(st, m);
+  if (cur & 1) rw_flush_jump(st, m); else rw_flush_chain(st, m);
   __syncwarp();
 
   // ---- write the row: 32 channels, lanes along the cells ----

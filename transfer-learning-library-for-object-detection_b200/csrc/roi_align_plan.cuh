@@ -19,22 +19,24 @@ constexpr int PL_MAXBINS = 8192;  // (image, plane row) bins of the backward row
 // emitted points at the dump cell behind the row (column `width`), so the scatter needs no
 // predicates.
 struct __align__(16) BwdCols {
-  float cw0[8], cw1[8], ms[8], mh[8];
+  float cw0[8], cw1[8];
+  int xoff[8];   // all-jump RoIs: byte offset of sample t's first cell (sites 2t, 2t+1 = xoff[t], xoff[t] + 4)
+  float ms[8], mh[8];
   int soff[16];  // site 2(t-1)+k (t = 1..8, k = 0/1): byte offset (ex[t] + k) * 4 in the row; width * 4 = dump
-  int all_jump;  // every sample is valid and starts a new pair of cells: the chain is the identity
-  int pad[3];
 };
-static_assert(sizeof(BwdCols) == 208, "BwdCols layout");
+constexpr unsigned BWDCOLS_JUMP_BYTES = 96;  // what an all-jump RoI needs: cw0, cw1, xoff
+static_assert(sizeof(BwdCols) == 224, "BwdCols layout");
 
 // One entry of a backward row list: gradient row (RoI, ph) adds weight * (its column scatter)
 // to the plane row the list belongs to.
 struct __align__(8) RowItem {
-  int roi_ph;  // (roi << 4) | ph
+  int roi_ph;  // (roi << 5) | (all_jump << 4) | ph; all_jump: every sample of the RoI's rows is valid
+               // and starts a new pair of cells, so the column chain is the identity
   float weight;
 };
 
 struct PlanLayout {
-  size_t cum, list, yrow, tabs, bwdx, rowcnt, rowptr, items, total;
+  size_t cum, list, yrow, jump, tabs, bwdx, rowcnt, rowptr, items, total;
 };
 __host__ __device__ inline size_t pl_align(size_t v) { return (v + 255) / 256 * 256; }
 __host__ __device__ inline PlanLayout plan_layout(int B, int R) {
@@ -43,6 +45,7 @@ __host__ __device__ inline PlanLayout plan_layout(int B, int R) {
   L.cum = off;    off = pl_align(off + (size_t)(B + 2) * 4);
   L.list = off;   off = pl_align(off + (size_t)R * 4);
   L.yrow = off;   off = pl_align(off + (size_t)R * 32);
+  L.jump = off;   off = pl_align(off + (size_t)R);
   L.tabs = off;   off = pl_align(off + (size_t)R * 512);
   L.bwdx = off;   off = pl_align(off + (size_t)R * sizeof(BwdCols));
   L.rowcnt = off; off = pl_align(off + (size_t)PL_MAXBINS * 4);
@@ -56,6 +59,7 @@ struct PlanPtrs {
   int* cum;        // [B + 2] exclusive prefix of RoIs per image; slot B = invalid image index
   int* list;       // [R] RoI indices sorted by image, stable
   short* yrow;     // [R][16] first sampled row of each output row, -1 if none
+  unsigned char* jump;  // [R] all-jump flag of the RoI's column chain
   float4* tabs;    // [R][32] rows 0..15: {row*W | -1, w0, w1, row | -1}; cols 16..31: {col | -1, w0, w1, col | -1}
   BwdCols* bwdx;   // [R]
   int* rowcnt;     // [B * H] items per (image, plane row)
@@ -69,6 +73,7 @@ __host__ __device__ inline PlanPtrs plan_ptrs(void* base, int B, int R) {
   q.cum = (int*)(p + L.cum);
   q.list = (int*)(p + L.list);
   q.yrow = (short*)(p + L.yrow);
+  q.jump = p + L.jump;
   q.tabs = (float4*)(p + L.tabs);
   q.bwdx = (BwdCols*)(p + L.bwdx);
   q.rowcnt = (int*)(p + L.rowcnt);
