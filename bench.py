@@ -287,7 +287,7 @@ def roi_align_cfg3(dev, iters=20):
     for name, kern, fn in (("plan", None, lambda: F.roi_align_plan(rois, x.shape, 8, 8, 1.0 / 16)),
                            ("fwd", "roi_align_fwd_planes_kernel",
                             lambda: F.roi_align_forward(x, rois, 8, 8, 1.0 / 16, plan=plan)),
-                           ("bwd", "roi_align_bwd_planes_kernel",
+                           ("bwd", "roi_align_bwd_rows_kernel",
                             lambda: F.roi_align_backward(top, rois, x.shape, 1.0 / 16, plan=plan))):
         for _ in range(3):
             fn()
@@ -426,7 +426,7 @@ def run_tlod(args):
         return n_roi * C * (64 + 49) * 4
     r_src, r_tgt = N_SRC * ROIS_SRC, N_TGT * ROIS_TGT
     alg = {"roi_align_fwd_planes_kernel": (roi_bytes(N_SRC, r_src) + roi_bytes(N_TGT, r_tgt)) / 2.0,
-           "roi_align_bwd_planes_kernel": (roi_bytes(N_SRC, r_src) + roi_bytes(N_TGT, r_tgt)) / 2.0,
+           "roi_align_bwd_rows_kernel": (roi_bytes(N_SRC, r_src) + roi_bytes(N_TGT, r_tgt)) / 2.0,
            "avgpool2x2_fwd_kernel": (pool_bytes(r_src) + pool_bytes(r_tgt)) / 2.0,
            "avgpool2x2_bwd_kernel": (pool_bytes(r_src) + pool_bytes(r_tgt)) / 2.0}
     traffic = {}

@@ -259,15 +259,30 @@ __global__ void __launch_bounds__(PL_THREADS)
   const int b = bin / H, y = bin - b * H;
   const int lo = __ldg(pl.cum + b), hi = __ldg(pl.cum + b + 1);
   RowItem* out = pl.items + before;
-  for (int base = lo; base < hi; base += 32) {
-    const int e = base + lane;
-    int n = 0;
-    unsigned hit0 = 0u, hit1 = 0u;  // bit ph: plane row y is the sample row's first / second row
-    if (e < hi) {
-      n = __ldg(pl.list + e);
-      const int4* yr = reinterpret_cast<const int4*>(pl.yrow + (size_t)n * 16);
-      const int4 q0 = __ldg(yr), q1 = __ldg(yr + 1);
-      const int w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+  constexpr int U = 8;  // chunks of 32 RoIs in flight: the list -> row table -> weight loads are dependent
+  for (int base = lo; base < hi; base += 32 * U) {
+    int n[U];
+    int4 q0[U], q1[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int e = base + 32 * u + lane;
+      n[u] = e < hi ? __ldg(pl.list + e) : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      q0[u] = make_int4(-1, -1, -1, -1);
+      q1[u] = q0[u];
+      if (n[u] >= 0) {
+        const int4* yr = reinterpret_cast<const int4*>(pl.yrow + (size_t)n[u] * 16);
+        q0[u] = __ldg(yr);
+        q1[u] = __ldg(yr + 1);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (base + 32 * u >= hi) break;
+      unsigned hit0 = 0u, hit1 = 0u;  // bit ph: plane row y is the sample row's first / second row
+      const int w[8] = {q0[u].x, q0[u].y, q0[u].z, q0[u].w, q1[u].x, q1[u].y, q1[u].z, q1[u].w};
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
         const int ys = (int)(short)((k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xffff));
@@ -276,26 +291,27 @@ __global__ void __launch_bounds__(PL_THREADS)
           if (ys + 1 == y) hit1 |= 1u << k;
         }
       }
-    }
-    unsigned both = hit0 | hit1;
-    const int cnt = __popc(both);
-    int incl = cnt;
+      unsigned both = hit0 | hit1;
+      const int cnt = __popc(both);
+      int incl = cnt;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += t;
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+      }
+      RowItem* o = out + incl - cnt;
+      const int key = n[u] >= 0 ? (n[u] << 5) | ((int)__ldg(pl.jump + n[u]) << 4) : 0;
+      while (both) {
+        const int ph = __ffs(both) - 1;
+        both &= both - 1u;
+        const float4 t = __ldg(pl.tabs + (size_t)n[u] * 32 + ph);
+        RowItem it;
+        it.roi_ph = key | ph;
+        it.weight = ((hit0 >> ph) & 1u) ? t.y : t.z;
+        *o++ = it;
+      }
+      out += __shfl_sync(0xffffffffu, incl, 31);
     }
-    RowItem* o = out + incl - cnt;
-    while (both) {
-      const int ph = __ffs(both) - 1;
-      both &= both - 1u;
-      const float4 t = __ldg(pl.tabs + (size_t)n * 32 + ph);
-      RowItem it;
-      it.roi_ph = (n << 5) | ((int)__ldg(pl.jump + n) << 4) | ph;
-      it.weight = ((hit0 >> ph) & 1u) ? t.y : t.z;
-      *o++ = it;
-    }
-    out += __shfl_sync(0xffffffffu, incl, 31);
   }
 }
 

@@ -28,7 +28,7 @@
 
 namespace tlod {
 
-constexpr int RW_STAGES = 4;
+constexpr int RW_STAGES = 3;  // ring depth per warp (2..4 measure the same; fewer = more warps per SM)
 constexpr int RW_TILE_BYTES = 32 * 32;  // 32 channels x one 32-byte gradient row
 constexpr int RW_STAGE_BYTES = RW_TILE_BYTES + 256;  // + BwdCols (208), padded: keeps the swizzle phase
 
@@ -160,15 +160,23 @@ __device__ __forceinline__ void rw_flush_chain(const RowCols& s, const float (&m
   for (int j = 0; j < 16; ++j) sts_f32(s.sa[j], o[j] + e[j]);
 }
 
-__global__ void __launch_bounds__(32, 16)
+// bytes of shared memory one warp owns: [stages][row: 32 channels x Ws floats][full barriers]
+__host__ __device__ inline unsigned rw_warp_bytes(int Ws, int stages) {
+  return (unsigned)(stages * RW_STAGE_BYTES + 32 * Ws * 4 + stages * 8 + 255) / 256u * 256u;
+}
+
+// blockDim.x = 32 * K: on small grids the K warps of a CTA split the row's item list (each with
+// its own copy of the row, summed when the row is written), so that the machine is filled.
+template <int K>
+__global__ void __launch_bounds__(32 * K)
     roi_align_bwd_rows_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ bottom_grad,
                               PlanPtrs pl, int B, int C, int H, int W, int Ws) {
   extern __shared__ __align__(1024) unsigned char smem_rw[];
-  // [stages][row: 32 channels x Ws floats][full barriers]
-  const unsigned stages = smem_u32(smem_rw);
-  float* row = reinterpret_cast<float*>(smem_rw + RW_STAGES * RW_STAGE_BYTES);
+  const int lane = lane_id(), wid = K > 1 ? warp_id() : 0;
+  unsigned char* mine = smem_rw + (size_t)wid * rw_warp_bytes(Ws, RW_STAGES);
+  const unsigned stages = smem_u32(mine);
+  float* row = reinterpret_cast<float*>(mine + RW_STAGES * RW_STAGE_BYTES);
   const unsigned bars = smem_u32(row + 32 * Ws);
-  const int lane = lane_id();
   const int y = blockIdx.x % H;
   const int rest = blockIdx.x / H;
   const int groups = C / 32;
@@ -185,8 +193,10 @@ __global__ void __launch_bounds__(32, 16)
   __syncwarp();
 
   const int bin = img * H + y;
-  const int cnt = __ldg(pl.rowcnt + bin);
-  const RowItem* __restrict__ items = pl.items + __ldg(pl.rowptr + bin);
+  const int cnt_all = __ldg(pl.rowcnt + bin);
+  const int seg_lo = (int)((long long)cnt_all * wid / K), seg_hi = (int)((long long)cnt_all * (wid + 1) / K);
+  const int cnt = seg_hi - seg_lo;  // this warp's share of the list
+  const RowItem* __restrict__ items = pl.items + __ldg(pl.rowptr + bin) + seg_lo;
 
   // lane's 32-byte row inside a tile, 16-byte halves swapped by the 32-byte swizzle
   const unsigned g_lo = (unsigned)(lane * 32 + (((lane >> 2) & 1) << 4));
@@ -202,6 +212,10 @@ __global__ void __launch_bounds__(32, 16)
   float ew[RW_STAGES];  // its row weight
   // all lanes run this (warp-uniform); one elected lane issues the asynchronous copies
   auto issue = [&](int j, int s) {
+    if ((j & 31) == 0 && j > 0) {  // the issue stream enters the next chunk
+      chunk = chunk_next;
+      chunk_next = j + 32 + lane < cnt ? __ldg(items2 + j + 32 + lane) : make_int2(0, 0);
+    }
     const int x = __shfl_sync(0xffffffffu, chunk.x, j & 31);
     const int n = x >> 4, ph = x & 15;  // n = (RoI << 1) | all_jump
     en[s] = n;
@@ -233,11 +247,6 @@ __global__ void __launch_bounds__(32, 16)
 
   for (int base = 0; base < cnt; base += RW_STAGES) {
     const unsigned parity = (unsigned)(base / RW_STAGES) & 1u;
-    if (((base + RW_STAGES) & 31) == 0) {  // the issue stream enters the next chunk (32 % RW_STAGES == 0)
-      chunk = chunk_next;
-      const int k = base + RW_STAGES + 32 + lane;
-      chunk_next = k < cnt ? __ldg(items2 + k) : make_int2(0, 0);
-    }
 #pragma unroll
     for (int s = 0; s < RW_STAGES; ++s) {
       const int i = base + s;
@@ -264,13 +273,20 @@ __global__ void __launch_bounds__(32, 16)
     }
   }
   if (cur & 1) rw_flush_jump(st, m); else rw_flush_chain(st, m);
-  __syncwarp();
+  if (K > 1) __syncthreads(); else __syncwarp();
 
-  // ---- write the row: 32 channels, lanes along the cells ----
+  // ---- write the row: warp k takes channels k, k + K, ...; lanes along the cells ----
   float* out = bottom_grad + (((size_t)img * C + c0) * H + y) * W;
   const size_t plane = (size_t)H * W;
-  for (int ch = 0; ch < 32; ++ch)
-    for (int x = lane; x < W; x += 32) out[ch * plane + x] = row[ch * Ws + x];
+  const float* row0 = reinterpret_cast<const float*>(smem_rw + RW_STAGES * RW_STAGE_BYTES);
+  const unsigned wstride = rw_warp_bytes(Ws, RW_STAGES) / 4u;
+  for (int ch = wid; ch < 32; ch += K)
+    for (int x = lane; x < W; x += 32) {
+      float v = row0[ch * Ws + x];
+#pragma unroll
+      for (int k = 1; k < K; ++k) v += row0[k * wstride + ch * Ws + x];
+      out[ch * plane + x] = v;
+    }
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
@@ -326,18 +342,24 @@ extern "C" int tlod_roi_align_backward(const float* top_grad, const float* rois,
   if (planned && plan_has_row_lists(batch, height) && channels % 32 == 0 && aligned_w == 8 &&
       ((uintptr_t)top_grad & 15) == 0) {
     const int Ws = (width + 1) | 1;  // + dump cell; odd stride: lane = channel is conflict free
-    const size_t smem = (size_t)RW_STAGES * RW_STAGE_BYTES + (size_t)32 * Ws * sizeof(float) + RW_STAGES * 8;
     const long long grid = (long long)batch * height * (channels / 32);
+    // small grids: K warps per row until ~12 warps per SM are in flight
+    int K = 1;
+    while (K < 4 && grid * K < 12LL * device_info().sm_count &&
+           (size_t)(K + 1) * rw_warp_bytes(Ws, RW_STAGES) <= (size_t)device_info().max_smem_optin)
+      ++K;
+    const size_t smem = (size_t)K * rw_warp_bytes(Ws, RW_STAGES);
     CUtensorMap tmap;
     if (grid <= 2147483647LL && smem <= (size_t)device_info().max_smem_optin &&
         make_grad_tmap(&tmap, top_grad, num_rois, channels, aligned_h)) {
-      cudaError_t e = cudaFuncSetAttribute(roi_align_bwd_rows_kernel,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      auto kern = K == 1 ? roi_align_bwd_rows_kernel<1> : K == 2 ? roi_align_bwd_rows_kernel<2>
+                  : K == 3 ? roi_align_bwd_rows_kernel<3> : roi_align_bwd_rows_kernel<4>;
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
       const PlanPtrs pl = plan_ptrs(const_cast<void*>(plan), batch, num_rois);
       {
         LaunchScope scope("roi_align_bwd_rows_kernel", st);
-        roi_align_bwd_rows_kernel<<<(int)grid, 32, smem, st>>>(tmap, bottom_grad, pl, batch, channels, height,
+        kern<<<(int)grid, 32 * K, smem, st>>>(tmap, bottom_grad, pl, batch, channels, height,
                                                               width, Ws);
       }
       return last_launch_status();
