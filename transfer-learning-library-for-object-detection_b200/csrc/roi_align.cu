@@ -32,6 +32,9 @@
 //    planes too large for shared memory, aligned size > 16, no plan): one CTA per
 //    (RoI, channel block), geometry hoisted to shared memory, coalesced output, fp32
 //    atomics in the backward.
+#include <cstring>
+
+#include "async_copy.cuh"
 #include "roi_align_plan.cuh"
 
 namespace tlod {
@@ -321,6 +324,8 @@ __global__ void __launch_bounds__(PL_THREADS)
 constexpr int PR_CH = 16;        // channels per slab == warps per CTA
 constexpr int PR_THREADS = 512;  // 16 warps
 
+constexpr int PR_TILE_BYTES = 2048;  // output staging tile of one warp: 16 channels x 4 rows x 8 floats
+
 struct PRShared {
   float4 wtab[PR_THREADS / 32][32];  // per-warp copy of the current RoI's tables
   int cur[4];                        // broadcast slots: image, slab, rank_lo, rank_hi
@@ -337,12 +342,19 @@ __host__ __device__ inline int pr_plane_stride(int h, int w) {
   return p;
 }
 
+__host__ __device__ inline size_t pr_tiles_offset(int Pp) {
+  return ((size_t)PR_CH * Pp * sizeof(float) + 1023) / 1024 * 1024;
+}
+
 __device__ __forceinline__ void st_global_v8(float* p, const float (&o)[8]) {
   asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(o[0]),
                "f"(o[1]), "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7])
                : "memory");
 }
 
+__device__ __forceinline__ void sts_v4(unsigned addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ float lds_f32(unsigned addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
@@ -361,10 +373,19 @@ __device__ __forceinline__ float lds_f32_imm(unsigned addr) {
 // with the even row stride that alone makes every gather bank-conflict free.
 // Addresses are 32-bit shared-window byte addresses; WP > 0 is the compile-time row stride
 // (the second row of a sample is then an immediate offset), WP == 0 the run-time one.
-template <int WP>
+//
+// TMA_OUT (aligned_h == 8): the rows are not stored from registers (fully sector-efficient, but
+// each 32-byte sector costs the LSU data pipe ~1.2 cycles) -- they go to a per-warp 2 KB tile
+// [16 channels][4 rows x 8] with two conflict-free STS.128 and leave with one TMA tensor store
+// per half RoI slab (rows 0-3, then rows 4-7; the output is (R, C, 2, 32) to the tensor map,
+// box 32 x 1 x 16 x 1, 128-byte swizzle: 16-byte chunk k of tile row r sits at chunk k ^ (r & 7)).
+// tile_row = shared address of this lane's channel row in the tile, cs = its swizzle key (c & 7).
+template <int WP, bool TMA_OUT>
 __device__ __forceinline__ void pr_fwd_roi_w8(unsigned plane_addr, int Wp_rt,
                                               const float4* __restrict__ wtab, int AH, int slot,
-                                              float* __restrict__ out_c /* channel c of the RoI */) {
+                                              float* __restrict__ out_c /* channel c of the RoI */,
+                                              const void* omap, unsigned tile, unsigned tile_row, unsigned cs,
+                                              int c0, int n) {
   unsigned ca[8], cb[8];
   float wp[8], wq[8];
 #pragma unroll
@@ -398,7 +419,25 @@ __device__ __forceinline__ void pr_fwd_roi_w8(unsigned plane_addr, int Wp_rt,
       const float t1 = fmaf(p11, wq[q], p10 * wp[q]);
       o[q] = fmaf(t1, r.z, t0 * r.y);
     }
-    if (2 * j + slot < AH) st_global_v8(out_c + ph * 8, o);
+    if (TMA_OUT) {
+      if ((j & 1) == 0) {  // the previous half's store must have read the tile
+        bulk_wait_read_all();
+        __syncwarp();
+      }
+      const unsigned k = (unsigned)((ph & 3) * 2);
+      sts_v4(tile_row + ((k ^ cs) << 4), o[0], o[1], o[2], o[3]);
+      sts_v4(tile_row + (((k | 1u) ^ cs) << 4), o[4], o[5], o[6], o[7]);
+      if (j & 1) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (elect_one()) {
+          tma_store_4d(omap, tile, 0, j >> 1, c0, n);
+          bulk_commit_group();
+        }
+      }
+    } else if (2 * j + slot < AH) {
+      st_global_v8(out_c + ph * 8, o);
+    }
   }
 }
 
@@ -430,19 +469,27 @@ __device__ __forceinline__ void pr_fwd_roi_any(const float* __restrict__ plane, 
 
 // W8: 0 = any aligned width (<= 16); 1 = aligned_w == 8; 76 = aligned_w == 8 and a padded row
 // stride of 76 floats (W = 75 or 76: the 600x1200 / stride-16 maps) as a compile-time constant.
-template <int W8>
+template <int W8, bool TMA_OUT>
 __global__ void __launch_bounds__(PR_THREADS, 1)
-    roi_align_fwd_planes_kernel(const float* __restrict__ features, float* __restrict__ output,
-                                PlanPtrs pl, int B, int C, int H, int W, int R, int AH, int AW,
-                                int Pp) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+    roi_align_fwd_planes_kernel(const __grid_constant__ CUtensorMap omap, const float* __restrict__ features,
+                                float* __restrict__ output, PlanPtrs pl, int B, int C, int H, int W, int R,
+                                int AH, int AW, int Pp) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // [planes][output tiles (TMA_OUT), 1024-byte aligned][PRShared]
   float* planes = reinterpret_cast<float*>(smem_raw);
-  PRShared& sh = *reinterpret_cast<PRShared*>(smem_raw + (size_t)PR_CH * Pp * sizeof(float));
+  const size_t tiles_off = pr_tiles_offset(Pp);
+  PRShared& sh = *reinterpret_cast<PRShared*>(
+      smem_raw + (TMA_OUT ? tiles_off + PR_TILE_BYTES * (PR_THREADS / 32) : (size_t)PR_CH * Pp * sizeof(float)));
   const int tid = threadIdx.x, lane = lane_id(), wid = warp_id();
   const int nslabs = C / PR_CH;
   const int P = H * W, S = AH * AW;
   const int Wp = pr_row_stride(W);
-  const int c = lane >> 1, slot = lane & 1;
+  // channel of the lane pair p = lane >> 1: bits (p0, p1, p2, p3) -> (c0, c2, c1, c3), so that the
+  // four channels of a quarter warp differ in c0 and c2 (the output tile's swizzle needs that)
+  const int pr = lane >> 1, slot = lane & 1;
+  const int c = (pr & 9) | ((pr & 2) << 1) | ((pr & 4) >> 1);
+  const unsigned tile = TMA_OUT ? smem_u32(smem_raw + tiles_off + (size_t)wid * PR_TILE_BYTES) : 0u;
+  const unsigned tile_row = tile + 128u * (unsigned)c, cs = (unsigned)(c & 7);
   const int* __restrict__ cum = pl.cum;
 
   // this CTA's contiguous range of (image, slab, RoI-rank) units
@@ -527,7 +574,8 @@ __global__ void __launch_bounds__(PR_THREADS, 1)
         if (W8 == 0)
           pr_fwd_roi_any(plane, Wp, wtab, AH, AW, slot, out_roi + (size_t)c * S);
         else
-          pr_fwd_roi_w8<(W8 > 1 ? W8 : 0)>(plane_addr, Wp, wtab, AH, slot, out_roi + (size_t)c * S);
+          pr_fwd_roi_w8<(W8 > 1 ? W8 : 0), TMA_OUT>(plane_addr, Wp, wtab, AH, slot, out_roi + (size_t)c * S,
+                                                     &omap, tile, tile_row, cs, c0, n);
         __syncwarp();
       }
       n = n2;
@@ -536,6 +584,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1)
     __syncthreads();
     u += (r_hi - r_lo);
   }
+  if (TMA_OUT) bulk_wait_all();  // the tiles must outlive their stores
 }
 
 // ===========================================================================
@@ -550,8 +599,23 @@ int roi_align_check_common(const void* a, const void* b, const void* c, int batc
   return TLOD_OK;
 }
 
-static size_t pr_smem_bytes(int h, int w) {
-  return (size_t)PR_CH * pr_plane_stride(h, w) * sizeof(float) + sizeof(PRShared);
+static size_t pr_smem_bytes(int h, int w, bool tma_out) {
+  const int Pp = pr_plane_stride(h, w);
+  if (tma_out) return pr_tiles_offset(Pp) + (size_t)PR_TILE_BYTES * (PR_THREADS / 32) + sizeof(PRShared);
+  return (size_t)PR_CH * Pp * sizeof(float) + sizeof(PRShared);
+}
+
+// (R, C, 8, 8) fp32 output seen as (R, C, 2, 32): box = rows 0-3 or 4-7 of 16 consecutive channels
+static bool make_out_tmap(CUtensorMap* map, float* output, int R, int C) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[4] = {32, 2, (cuuint64_t)C, (cuuint64_t)R};
+  const cuuint64_t strides[3] = {128, 256, (cuuint64_t)C * 256};
+  const cuuint32_t box[4] = {32, 1, (cuuint32_t)PR_CH, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, output, dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 int roi_align_generic_launch(bool backward, const float* src, const float* rois, float* dst, int batch,
@@ -632,22 +696,29 @@ extern "C" int tlod_roi_align_forward(const float* features, const float* rois, 
   if (plan && (plan_bytes < tlod_roi_align_plan_bytes(batch, num_rois) || ((uintptr_t)plan & 255)))
     return TLOD_ERR_WORKSPACE;
   if (planned && channels % PR_CH == 0 &&
-      pr_smem_bytes(height, width) <= (size_t)device_info().max_smem_optin) {
+      pr_smem_bytes(height, width, false) <= (size_t)device_info().max_smem_optin) {
     const int Pp = pr_plane_stride(height, width);
-    const size_t smem = pr_smem_bytes(height, width);
     const long long units = (long long)(channels / PR_CH) * num_rois;
     int grid = device_info().sm_count;
     if ((long long)grid > units) grid = (int)units;
     const bool w8 = aligned_w == 8 && ((uintptr_t)output & 31) == 0;
-    auto kern = !w8 ? roi_align_fwd_planes_kernel<0>
-                    : (pr_row_stride(width) == 76 ? roi_align_fwd_planes_kernel<76>
-                                                  : roi_align_fwd_planes_kernel<1>);
+    // 8x8 outputs leave through per-warp staging tiles and TMA stores when the tiles fit beside the planes
+    CUtensorMap omap;
+    memset(&omap, 0, sizeof(omap));
+    const bool tma_out = w8 && aligned_h == 8 && ((uintptr_t)output & 127) == 0 &&
+                         pr_smem_bytes(height, width, true) <= (size_t)device_info().max_smem_optin &&
+                         make_out_tmap(&omap, output, num_rois, channels);
+    const size_t smem = pr_smem_bytes(height, width, tma_out);
+    const bool w76 = pr_row_stride(width) == 76;
+    auto kern = !w8 ? roi_align_fwd_planes_kernel<0, false>
+                : tma_out ? (w76 ? roi_align_fwd_planes_kernel<76, true> : roi_align_fwd_planes_kernel<1, true>)
+                          : (w76 ? roi_align_fwd_planes_kernel<76, false> : roi_align_fwd_planes_kernel<1, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     const PlanPtrs pl = plan_ptrs(const_cast<void*>(plan), batch, num_rois);
     {
       LaunchScope scope("roi_align_fwd_planes_kernel", st);
-      kern<<<grid, PR_THREADS, smem, st>>>(features, output, pl, batch, channels, height, width,
+      kern<<<grid, PR_THREADS, smem, st>>>(omap, features, output, pl, batch, channels, height, width,
                                            num_rois, aligned_h, aligned_w, Pp);
     }
     return last_launch_status();

@@ -22,8 +22,7 @@
 //     emitted point at a dump cell behind the row).
 // Warps are independent: no block-wide synchronisation anywhere, and the grid (B * H * C/32
 // one-warp CTAs) is balanced by the hardware scheduler.
-#include <cuda.h>
-
+#include "async_copy.cuh"
 #include "roi_align_plan.cuh"
 
 namespace tlod {
@@ -32,54 +31,6 @@ constexpr int RW_STAGES = 3;  // ring depth per warp (2..4 measure the same; few
 constexpr int RW_TILE_BYTES = 32 * 32;  // 32 channels x one 32-byte gradient row
 constexpr int RW_STAGE_BYTES = RW_TILE_BYTES + 256;  // + BwdCols (208), padded: keeps the swizzle phase
 
-__device__ __forceinline__ unsigned smem_u32(const void* p) {
-  return (unsigned)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-  unsigned done = 0;
-  // bounded: a lost TMA transaction must fault the launch, not hang the device
-  for (unsigned spins = 0; !done; ++spins) {
-    if (spins > (1u << 24)) __trap();
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  }
-}
-__device__ __forceinline__ bool elect_one() {
-  unsigned pred;
-  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void bulk_load(unsigned smem_dst, const void* gsrc, unsigned bytes, unsigned bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_dst),
-               "l"(gsrc), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(unsigned smem_dst, const void* tmap, unsigned bar, int c0, int c1,
-                                            int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_dst),
-      "l"((unsigned long long)tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_4d(const void* tmap, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(
-                   (unsigned long long)tmap),
-               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}
 __device__ __forceinline__ float lds_f32(unsigned addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
@@ -287,23 +238,6 @@ __global__ void __launch_bounds__(32 * K)
       for (int k = 1; k < K; ++k) v += row0[k * wstride + ch * Ws + x];
       out[ch * plane + x] = v;
     }
-}
-
-// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                  CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = []() -> EncodeTiledFn {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &p, 12000, cudaEnableDefault, &q) !=
-            cudaSuccess || q != cudaDriverEntryPointSuccess)
-      return nullptr;
-    return (EncodeTiledFn)p;
-  }();
-  return fn;
 }
 
 // (R, C, AH, 8) fp32 gradient tensor; box = one 8-wide row of 32 consecutive channels
