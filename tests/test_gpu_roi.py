@@ -12,9 +12,10 @@ from util import bits_equal, edge_rois, features, rel_err
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
-# (B, C, H, W, R, AH, AW, scale): plane-resident forward (AW == 8 fast path and general
-# sampling 7x7 / 3x5 / 14x14), band-resident backward (AW == 8, C % 32 == 0), and shapes that
-# fall back to the generic kernels (channels % 16, planes too big for shared memory)
+# (B, C, H, W, R, AH, AW, scale): plane-resident forward (AW == 8 fast path, TMA-stored 8x8
+# tiles, and general sampling 7x7 / 3x5 / 14x14), row-resident backward (AW == 8, C % 32 == 0,
+# B * H <= 8192 row lists; 1-4 warps per row depending on the grid), and shapes that fall back
+# to the generic kernels (channels % 16, planes too big for shared memory, too many row bins)
 ALIGN_CASES = {
     "cfg1_vgg_conv5": (1, 64, 37, 75, 128, 8, 8, 1 / 16),
     "multi_image_res_conv4": (4, 32, 38, 75, 200, 8, 8, 1 / 16),
@@ -29,6 +30,10 @@ ALIGN_CASES = {
     "bwd_partial_channel_group": (2, 160, 20, 31, 64, 8, 8, 1 / 16),  # 128 + 32 channels
     "bwd_one_warp_group": (3, 32, 38, 75, 96, 8, 8, 1 / 16),
     "tall_tile_6x8": (2, 64, 37, 75, 80, 6, 8, 1 / 16),
+    "bwd_wide_rows": (1, 32, 60, 300, 40, 8, 8, 1 / 4),              # 38 KB of row per warp, 4 warps per row
+    "bwd_too_many_row_bins": (300, 32, 30, 20, 400, 8, 8, 1 / 16),   # B * H > 8192: generic backward
+    "bwd_one_warp_per_row": (8, 256, 38, 75, 300, 8, 8, 1 / 16),     # grid large enough for K = 1
+    "bwd_long_row_lists": (1, 32, 12, 20, 900, 8, 8, 1 / 16),        # > 32-entry chunks, every ph per row
 }
 
 
