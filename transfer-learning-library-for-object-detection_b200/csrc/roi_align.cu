@@ -245,76 +245,100 @@ __global__ void __launch_bounds__(PL_THREADS)
   }
 }
 
-// Backward row lists.  One warp per (image, plane row) bin: its first item = sum of the counts
-// of the bins before it; then it walks the image's RoIs in list order, 32 at a time, and writes
-// the items (RoI, ph, row weight) whose sample row touches this plane row, in (RoI, ph) order --
+// Backward row lists.  One CTA per (image, plane row) bin: its first item = sum of the counts of
+// the bins before it; its 8 warps take the image's RoIs in list order, 32 per warp and round
+// (all the dependent list -> row table loads of a pass are in flight at once), find the sample
+// rows that touch this plane row, and write the items (RoI, ph, row weight) in (RoI, ph) order --
 // a fixed order, so the backward sums are bitwise reproducible.
+constexpr int PLR_WARPS = PL_THREADS / 32;
+constexpr int PLR_ROUNDS = 4;  // 32-RoI chunks per warp and pass: a pass covers 1024 RoIs
+
 __global__ void __launch_bounds__(PL_THREADS)
     roi_align_plan_rows_kernel(PlanPtrs pl, int B, int H, int AH) {
-  const int lane = lane_id();
-  const int bin = blockIdx.x * (PL_THREADS / 32) + warp_id();
-  if (bin >= B * H) return;
-  int before = 0;
-  for (int k = lane; k < bin; k += 32) before += __ldg(pl.rowcnt + k);
+  __shared__ int chunk_cnt[PLR_WARPS * PLR_ROUNDS];
+  __shared__ int bin_base;
+  const int lane = lane_id(), wid = warp_id();
+  const int bin = blockIdx.x;
+  if (wid == 0) {
+    int before = 0;
+    for (int k = lane; k < bin; k += 32) before += __ldg(pl.rowcnt + k);
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) before += __shfl_xor_sync(0xffffffffu, before, d);
-  if (lane == 0) pl.rowptr[bin] = before;
+    for (int d = 16; d > 0; d >>= 1) before += __shfl_xor_sync(0xffffffffu, before, d);
+    if (lane == 0) {
+      pl.rowptr[bin] = before;
+      bin_base = before;
+    }
+  }
   const int b = bin / H, y = bin - b * H;
   const int lo = __ldg(pl.cum + b), hi = __ldg(pl.cum + b + 1);
-  RowItem* out = pl.items + before;
-  constexpr int U = 8;  // chunks of 32 RoIs in flight: the list -> row table -> weight loads are dependent
-  for (int base = lo; base < hi; base += 32 * U) {
-    int n[U];
-    int4 q0[U], q1[U];
+  int written = 0;  // items of the passes before this one
+  for (int base = lo; base < hi; base += 32 * PLR_WARPS * PLR_ROUNDS) {
+    // chunk c = r * PLR_WARPS + wid of this pass: RoIs base + 32 c .. base + 32 c + 31
+    int n[PLR_ROUNDS];
+    int4 q0[PLR_ROUNDS], q1[PLR_ROUNDS];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int e = base + 32 * u + lane;
-      n[u] = e < hi ? __ldg(pl.list + e) : -1;
+    for (int r = 0; r < PLR_ROUNDS; ++r) {
+      const int e = base + 32 * (r * PLR_WARPS + wid) + lane;
+      n[r] = e < hi ? __ldg(pl.list + e) : -1;
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      q0[u] = make_int4(-1, -1, -1, -1);
-      q1[u] = q0[u];
-      if (n[u] >= 0) {
-        const int4* yr = reinterpret_cast<const int4*>(pl.yrow + (size_t)n[u] * 16);
-        q0[u] = __ldg(yr);
-        q1[u] = __ldg(yr + 1);
+    for (int r = 0; r < PLR_ROUNDS; ++r) {
+      q0[r] = make_int4(-1, -1, -1, -1);
+      q1[r] = q0[r];
+      if (n[r] >= 0) {
+        const int4* yr = reinterpret_cast<const int4*>(pl.yrow + (size_t)n[r] * 16);
+        q0[r] = __ldg(yr);
+        q1[r] = __ldg(yr + 1);
       }
     }
+    unsigned hit0[PLR_ROUNDS], hit1[PLR_ROUNDS];  // bit ph: plane row y is the sample row's first / second row
+    int incl[PLR_ROUNDS];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (base + 32 * u >= hi) break;
-      unsigned hit0 = 0u, hit1 = 0u;  // bit ph: plane row y is the sample row's first / second row
-      const int w[8] = {q0[u].x, q0[u].y, q0[u].z, q0[u].w, q1[u].x, q1[u].y, q1[u].z, q1[u].w};
+    for (int r = 0; r < PLR_ROUNDS; ++r) {
+      hit0[r] = hit1[r] = 0u;
+      const int w[8] = {q0[r].x, q0[r].y, q0[r].z, q0[r].w, q1[r].x, q1[r].y, q1[r].z, q1[r].w};
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
         const int ys = (int)(short)((k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xffff));
         if (k < AH && ys >= 0) {
-          if (ys == y) hit0 |= 1u << k;
-          if (ys + 1 == y) hit1 |= 1u << k;
+          if (ys == y) hit0[r] |= 1u << k;
+          if (ys + 1 == y) hit1[r] |= 1u << k;
         }
       }
-      unsigned both = hit0 | hit1;
-      const int cnt = __popc(both);
-      int incl = cnt;
+      int v = __popc(hit0[r] | hit1[r]);
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += t;
+        const int t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += t;
       }
-      RowItem* o = out + incl - cnt;
-      const int key = n[u] >= 0 ? (n[u] << 5) | ((int)__ldg(pl.jump + n[u]) << 4) : 0;
-      while (both) {
-        const int ph = __ffs(both) - 1;
-        both &= both - 1u;
-        const float4 t = __ldg(pl.tabs + (size_t)n[u] * 32 + ph);
-        RowItem it;
-        it.roi_ph = key | ph;
-        it.weight = ((hit0 >> ph) & 1u) ? t.y : t.z;
-        *o++ = it;
-      }
-      out += __shfl_sync(0xffffffffu, incl, 31);
+      incl[r] = v;
+      if (lane == 31) chunk_cnt[r * PLR_WARPS + wid] = v;
     }
+    __syncthreads();
+    int pass_total = 0;
+#pragma unroll
+    for (int c = 0; c < PLR_WARPS * PLR_ROUNDS; ++c) pass_total += chunk_cnt[c];
+#pragma unroll
+    for (int r = 0; r < PLR_ROUNDS; ++r) {
+      unsigned both = hit0[r] | hit1[r];
+      if (both) {
+        int pos = bin_base + written + incl[r] - __popc(both);
+        for (int c = 0; c < r * PLR_WARPS + wid; ++c) pos += chunk_cnt[c];
+        RowItem* o = pl.items + pos;
+        const int key = (n[r] << 5) | ((int)__ldg(pl.jump + n[r]) << 4);
+        while (both) {
+          const int ph = __ffs(both) - 1;
+          both &= both - 1u;
+          const float4 t = __ldg(pl.tabs + (size_t)n[r] * 32 + ph);
+          RowItem it;
+          it.roi_ph = key | ph;
+          it.weight = ((hit0[r] >> ph) & 1u) ? t.y : t.z;
+          *o++ = it;
+        }
+      }
+    }
+    written += pass_total;
+    __syncthreads();  // chunk_cnt is rewritten by the next pass
   }
 }
 
@@ -677,8 +701,7 @@ extern "C" int tlod_roi_align_plan(const float* rois, int batch, int height, int
   if (rc != TLOD_OK || !rows) return rc;
   {
     LaunchScope scope("roi_align_plan_rows_kernel", st);
-    roi_align_plan_rows_kernel<<<(bins + PL_THREADS / 32 - 1) / (PL_THREADS / 32), PL_THREADS, 0, st>>>(
-        pl, batch, height, aligned_h);
+    roi_align_plan_rows_kernel<<<bins, PL_THREADS, 0, st>>>(pl, batch, height, aligned_h);
   }
   return last_launch_status();
 }
