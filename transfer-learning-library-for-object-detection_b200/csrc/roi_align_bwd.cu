@@ -151,7 +151,8 @@ __global__ void __launch_bounds__(32 * K)
 
   // lane's 32-byte row inside a tile, 16-byte halves swapped by the 32-byte swizzle
   const unsigned g_lo = (unsigned)(lane * 32 + (((lane >> 2) & 1) << 4));
-  const unsigned g_hi = g_lo ^ 16u;
+  unsigned g_hi;  // = g_lo ^ 16, kept in a register (the compiler would recompute it from %tid per item)
+  asm volatile("xor.b32 %0, %1, 16;" : "=r"(g_hi) : "r"(g_lo));
 
   // The issue stream reads the list sequentially: 32 entries per coalesced load, one chunk ahead,
   // handed out by shuffles (no global-memory latency on the per-item path).
