@@ -68,12 +68,13 @@ int tlod_profile_get(int index, const char** name, double* total_ms, long long* 
 /*   (kernels lib/model/roi_align/src/roi_align_kernel.cu:15-70, :94-143)     */
 /* ------------------------------------------------------------------------ */
 /* RoIAlign plan: everything that depends only on (rois, map geometry, aligned size):
- * per-RoI sampling tables, the RoI indices stably sorted by image, per-image offsets and
- * the backward column chains.  Build it once per `rois` tensor with tlod_roi_align_plan
+ * per-RoI sampling tables, the RoI indices stably sorted by image, per-image offsets, the
+ * backward column chains and, per (image, map row), the list of gradient rows that feed it.  Build it once per `rois` tensor with tlod_roi_align_plan
  * and pass it to the forward and the backward call (same batch, height, width, num_rois,
  * aligned_h, aligned_w, spatial_scale).  `plan` must be 256-byte aligned and at least
  * tlod_roi_align_plan_bytes(batch, num_rois) bytes.  Limits of the planned (shared-memory
- * resident, atomic-free) kernels: batch <= 1024, aligned_h/w <= 16; outside them, or with
+ * resident, atomic-free) kernels: batch <= 1024, aligned_h/w <= 16 (backward also:
+ * aligned_w == 8, channels % 32 == 0, batch * height <= 8192); outside them, or with
  * plan == NULL, the forward/backward entry points use the generic kernels (one CTA per
  * RoI and channel block; fp32 atomics in the backward). */
 size_t tlod_roi_align_plan_bytes(int batch, int num_rois);
