@@ -34,6 +34,7 @@ ALIGN_CASES = {
     "bwd_too_many_row_bins": (300, 32, 30, 20, 400, 8, 8, 1 / 16),   # B * H > 8192: generic backward
     "bwd_one_warp_per_row": (8, 256, 38, 75, 300, 8, 8, 1 / 16),     # grid large enough for K = 1
     "bwd_long_row_lists": (1, 32, 12, 20, 900, 8, 8, 1 / 16),        # > 32-entry chunks, every ph per row
+    "bwd_two_channels_per_lane": (16, 256, 38, 75, 200, 8, 8, 1 / 16),  # >= 2 waves of 64-channel warps
 }
 
 

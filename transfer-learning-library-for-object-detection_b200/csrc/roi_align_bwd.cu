@@ -28,8 +28,17 @@
 namespace tlod {
 
 constexpr int RW_STAGES = 3;  // ring depth per warp (2..4 measure the same; fewer = more warps per SM)
-constexpr int RW_TILE_BYTES = 32 * 32;  // 32 channels x one 32-byte gradient row
-constexpr int RW_STAGE_BYTES = RW_TILE_BYTES + 256;  // + BwdCols (208), padded: keeps the swizzle phase
+constexpr int RW_META_BYTES = 256;  // BwdCols (224), padded: keeps the tiles' swizzle phase
+// CPL = channels per lane (1 or 2): a warp owns 32 * CPL channels of its row.  With CPL = 2 a
+// cell holds the pair (channel lane, channel lane + 32) as a float2: one 64-bit shared-memory
+// access updates both, and the per-item bookkeeping and the column state are paid once per 64
+// channels -- but a warp needs twice the shared memory, so it is used on large grids only.
+__host__ __device__ constexpr int rw_tile_bytes(int cpl) { return 32 * 32 * cpl; }  // 32-byte rows
+__host__ __device__ constexpr int rw_stage_bytes(int cpl) { return rw_tile_bytes(cpl) + RW_META_BYTES; }
+// bytes of shared memory one warp owns: [stages][row: 32 lanes x Ws cells x CPL floats][full barriers]
+__host__ __device__ inline unsigned rw_warp_bytes(int Ws, int cpl) {
+  return (unsigned)(RW_STAGES * rw_stage_bytes(cpl) + 32 * Ws * 4 * cpl + RW_STAGES * 8 + 255) / 256u * 256u;
+}
 
 __device__ __forceinline__ float lds_f32(unsigned addr) {
   float v;
@@ -39,10 +48,40 @@ __device__ __forceinline__ float lds_f32(unsigned addr) {
 __device__ __forceinline__ void sts_f32(unsigned addr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
+__device__ __forceinline__ float2 lds_v2(unsigned addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_v2(unsigned addr, float a, float b) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
 __device__ __forceinline__ float4 lds_v4(unsigned addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
+}
+// one cell of the lane's row: CPL floats
+template <int CPL>
+struct Cell {
+  float v[CPL];
+};
+template <int CPL>
+__device__ __forceinline__ Cell<CPL> cell_load(unsigned addr) {
+  Cell<CPL> c;
+  if (CPL == 1) {
+    c.v[0] = lds_f32(addr);
+  } else {
+    const float2 t = lds_v2(addr);
+    c.v[0] = t.x;
+    c.v[CPL - 1] = t.y;
+  }
+  return c;
+}
+template <int CPL>
+__device__ __forceinline__ void cell_store(unsigned addr, const Cell<CPL>& c) {
+  if (CPL == 1) sts_f32(addr, c.v[0]);
+  else sts_v2(addr, c.v[0], c.v[CPL - 1]);
 }
 
 // column state of the current RoI, for this lane's row
@@ -55,92 +94,102 @@ struct RowCols {
 __device__ __forceinline__ void rw_unpack(float (&d)[8], const float4 a, const float4 b) {
   d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
 }
+// plan offsets are bytes of a one-float cell: scaled by CPL here
+template <int CPL>
 __device__ __forceinline__ void rw_unpack_addr(unsigned* d, const float4 a, unsigned row_addr) {
-  d[0] = row_addr + (unsigned)__float_as_int(a.x); d[1] = row_addr + (unsigned)__float_as_int(a.y);
-  d[2] = row_addr + (unsigned)__float_as_int(a.z); d[3] = row_addr + (unsigned)__float_as_int(a.w);
+  d[0] = row_addr + (unsigned)__float_as_int(a.x) * CPL; d[1] = row_addr + (unsigned)__float_as_int(a.y) * CPL;
+  d[2] = row_addr + (unsigned)__float_as_int(a.z) * CPL; d[3] = row_addr + (unsigned)__float_as_int(a.w) * CPL;
 }
 
 // all lanes read the same bytes (broadcast).  JUMP: the 96-byte head of BwdCols; else all of it.
-template <bool JUMP>
+template <bool JUMP, int CPL>
 __device__ __forceinline__ void rw_load_cols(RowCols& s, unsigned meta, unsigned row_addr) {
   rw_unpack(s.cw0, lds_v4(meta), lds_v4(meta + 16));
   rw_unpack(s.cw1, lds_v4(meta + 32), lds_v4(meta + 48));
   if (JUMP) {
-    rw_unpack_addr(s.sa, lds_v4(meta + 64), row_addr);
-    rw_unpack_addr(s.sa + 4, lds_v4(meta + 80), row_addr);
+    rw_unpack_addr<CPL>(s.sa, lds_v4(meta + 64), row_addr);
+    rw_unpack_addr<CPL>(s.sa + 4, lds_v4(meta + 80), row_addr);
   } else {
     rw_unpack(s.ms, lds_v4(meta + 96), lds_v4(meta + 112));
     rw_unpack(s.mh, lds_v4(meta + 128), lds_v4(meta + 144));
 #pragma unroll
-    for (int i = 0; i < 4; ++i) rw_unpack_addr(s.sa + 4 * i, lds_v4(meta + 160 + 16 * i), row_addr);
+    for (int i = 0; i < 4; ++i) rw_unpack_addr<CPL>(s.sa + 4 * i, lds_v4(meta + 160 + 16 * i), row_addr);
   }
 }
 
 // The RoI's summed gradient rows m -> values of the 16 column sites -> added to the row.
 // All-jump RoIs: sample t owns cells (x_t, x_t + 1) alone.
-__device__ __forceinline__ void rw_flush_jump(const RowCols& s, const float (&m)[8]) {
-  float o0[8], o1[8];
+template <int CPL>
+__device__ __forceinline__ void rw_flush_jump(const RowCols& s, const float (&m)[CPL][8]) {
+  Cell<CPL> o0[8], o1[8];
 #pragma unroll
   for (int t = 0; t < 8; ++t) {
-    o0[t] = lds_f32(s.sa[t]);
-    o1[t] = lds_f32(s.sa[t] + 4u);
+    o0[t] = cell_load<CPL>(s.sa[t]);
+    o1[t] = cell_load<CPL>(s.sa[t] + 4u * CPL);
   }
 #pragma unroll
   for (int t = 0; t < 8; ++t) {
-    sts_f32(s.sa[t], fmaf(m[t], s.cw0[t], o0[t]));
-    sts_f32(s.sa[t] + 4u, fmaf(m[t], s.cw1[t], o1[t]));
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      o0[t].v[k] = fmaf(m[k][t], s.cw0[t], o0[t].v[k]);
+      o1[t].v[k] = fmaf(m[k][t], s.cw1[t], o1[t].v[k]);
+    }
+    cell_store<CPL>(s.sa[t], o0[t]);
+    cell_store<CPL>(s.sa[t] + 4u * CPL, o1[t]);
   }
 }
 // General RoIs: the chain of BwdCols.  The loads of the old values are issued first, so that the
 // serial chain runs under their latency; all 16 cells are distinct (or dump cells), so the order
 // is free.
-__device__ __forceinline__ void rw_flush_chain(const RowCols& s, const float (&m)[8]) {
-  float o[16], e[16];
+template <int CPL>
+__device__ __forceinline__ void rw_flush_chain(const RowCols& s, const float (&m)[CPL][8]) {
+  Cell<CPL> o[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) o[j] = lds_f32(s.sa[j]);
-  float a0 = 0.f, a1 = 0.f;
+  for (int j = 0; j < 16; ++j) o[j] = cell_load<CPL>(s.sa[j]);
 #pragma unroll
-  for (int t = 0; t < 8; ++t) {
-    if (t > 0) { e[2 * (t - 1)] = a0; e[2 * (t - 1) + 1] = a1; }
-    const float na0 = fmaf(s.ms[t], a0, fmaf(s.mh[t], a1, m[t] * s.cw0[t]));
-    a1 = fmaf(s.ms[t], a1, m[t] * s.cw1[t]);
-    a0 = na0;
+  for (int k = 0; k < CPL; ++k) {
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      if (t > 0) { o[2 * (t - 1)].v[k] += a0; o[2 * (t - 1) + 1].v[k] += a1; }
+      const float na0 = fmaf(s.ms[t], a0, fmaf(s.mh[t], a1, m[k][t] * s.cw0[t]));
+      a1 = fmaf(s.ms[t], a1, m[k][t] * s.cw1[t]);
+      a0 = na0;
+    }
+    o[14].v[k] += a0;
+    o[15].v[k] += a1;
   }
-  e[14] = a0; e[15] = a1;
 #pragma unroll
-  for (int j = 0; j < 16; ++j) sts_f32(s.sa[j], o[j] + e[j]);
-}
-
-// bytes of shared memory one warp owns: [stages][row: 32 channels x Ws floats][full barriers]
-__host__ __device__ inline unsigned rw_warp_bytes(int Ws, int stages) {
-  return (unsigned)(stages * RW_STAGE_BYTES + 32 * Ws * 4 + stages * 8 + 255) / 256u * 256u;
+  for (int j = 0; j < 16; ++j) cell_store<CPL>(s.sa[j], o[j]);
 }
 
 // blockDim.x = 32 * K: on small grids the K warps of a CTA split the row's item list (each with
 // its own copy of the row, summed when the row is written), so that the machine is filled.
-template <int K>
+template <int K, int CPL>
 __global__ void __launch_bounds__(32 * K)
     roi_align_bwd_rows_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ bottom_grad,
                               PlanPtrs pl, int B, int C, int H, int W, int Ws) {
+  static_assert(CPL == 1 || (CPL == 2 && K == 1), "two channels per lane: one warp per row");
+  constexpr int TILE = rw_tile_bytes(CPL), STAGE = rw_stage_bytes(CPL), CH = 32 * CPL;
   extern __shared__ __align__(1024) unsigned char smem_rw[];
   const int lane = lane_id(), wid = K > 1 ? warp_id() : 0;
-  unsigned char* mine = smem_rw + (size_t)wid * rw_warp_bytes(Ws, RW_STAGES);
+  unsigned char* mine = smem_rw + (size_t)wid * rw_warp_bytes(Ws, CPL);
   const unsigned stages = smem_u32(mine);
-  float* row = reinterpret_cast<float*>(mine + RW_STAGES * RW_STAGE_BYTES);
-  const unsigned bars = smem_u32(row + 32 * Ws);
+  float* row = reinterpret_cast<float*>(mine + RW_STAGES * STAGE);
+  const unsigned bars = smem_u32(row + 32 * Ws * CPL);
   const int y = blockIdx.x % H;
   const int rest = blockIdx.x / H;
-  const int groups = C / 32;
+  const int groups = C / CH;
   const int grp = rest % groups, img = rest / groups;
-  const int c0 = grp * 32;
-  const unsigned row_addr = smem_u32(row + lane * Ws);
+  const int c0 = grp * CH;
+  const unsigned row_addr = smem_u32(row + lane * Ws * CPL);
 
   if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < RW_STAGES; ++s) mbar_init(bars + 8u * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = lane; i < 32 * Ws; i += 32) row[i] = 0.f;
+  for (int i = lane; i < 32 * Ws * CPL; i += 32) row[i] = 0.f;
   __syncwarp();
 
   const int bin = img * H + y;
@@ -149,7 +198,8 @@ __global__ void __launch_bounds__(32 * K)
   const int cnt = seg_hi - seg_lo;  // this warp's share of the list
   const RowItem* __restrict__ items = pl.items + __ldg(pl.rowptr + bin) + seg_lo;
 
-  // lane's 32-byte row inside a tile, 16-byte halves swapped by the 32-byte swizzle
+  // lane's 32-byte row inside a tile, 16-byte halves swapped by the 32-byte swizzle (the second
+  // channel's row, 32 rows further, has the same swizzle phase)
   const unsigned g_lo = (unsigned)(lane * 32 + (((lane >> 2) & 1) << 4));
   unsigned g_hi;  // = g_lo ^ 16, kept in a register (the compiler would recompute it from %tid per item)
   asm volatile("xor.b32 %0, %1, 16;" : "=r"(g_hi) : "r"(g_lo));
@@ -159,8 +209,8 @@ __global__ void __launch_bounds__(32 * K)
   const int2* __restrict__ items2 = reinterpret_cast<const int2*>(items);
   int2 chunk = lane < cnt ? __ldg(items2 + lane) : make_int2(0, 0);
   int2 chunk_next = 32 + lane < cnt ? __ldg(items2 + 32 + lane) : make_int2(0, 0);
-  int issue_prev = -1;  // RoI of the item issued last (its BwdCols travel with the first item of a RoI)
-  int en[RW_STAGES];    // (RoI << 1) | all_jump of the item in stage s
+  int issue_prev = -1;  // key of the item issued last (the BwdCols travel with the first item of a RoI)
+  int en[RW_STAGES];    // key = (RoI << 1) | all_jump of the item in stage s
   float ew[RW_STAGES];  // its row weight
   // all lanes run this (warp-uniform); one elected lane issues the asynchronous copies
   auto issue = [&](int j, int s) {
@@ -169,15 +219,15 @@ __global__ void __launch_bounds__(32 * K)
       chunk_next = j + 32 + lane < cnt ? __ldg(items2 + j + 32 + lane) : make_int2(0, 0);
     }
     const int x = __shfl_sync(0xffffffffu, chunk.x, j & 31);
-    const int n = x >> 4, ph = x & 15;  // n = (RoI << 1) | all_jump
+    const int n = x >> 4, ph = x & 15;  // n = key
     en[s] = n;
     ew[s] = __int_as_float(__shfl_sync(0xffffffffu, chunk.y, j & 31));
-    const unsigned bar = bars + 8u * s, stg = stages + (unsigned)(s * RW_STAGE_BYTES);
+    const unsigned bar = bars + 8u * s, stg = stages + (unsigned)(s * STAGE);
     const unsigned cols = n == issue_prev ? 0u : ((n & 1) ? BWDCOLS_JUMP_BYTES : (unsigned)sizeof(BwdCols));
     if (elect_one()) {
-      mbar_arrive_expect_tx(bar, RW_TILE_BYTES + cols);
+      mbar_arrive_expect_tx(bar, TILE + cols);
       tma_load_4d(stg, &tmap, bar, 0, ph, c0, n >> 1);
-      if (cols) bulk_load(stg + RW_TILE_BYTES, pl.bwdx + (n >> 1), cols, bar);
+      if (cols) bulk_load(stg + TILE, pl.bwdx + (n >> 1), cols, bar);
     }
     issue_prev = n;
   };
@@ -191,11 +241,13 @@ __global__ void __launch_bounds__(32 * K)
 #pragma unroll
   for (int t = 0; t < 8; ++t) { st.cw0[t] = 0.f; st.cw1[t] = 0.f; st.ms[t] = 0.f; st.mh[t] = 0.f; }
 #pragma unroll
-  for (int j = 0; j < 16; ++j) st.sa[j] = row_addr + 4u * (unsigned)W;
+  for (int j = 0; j < 16; ++j) st.sa[j] = row_addr + 4u * CPL * (unsigned)W;
   int cur = -1;  // never an item's key; odd: the first flush takes the all-jump path, into the dump cell
-  float m[8];
+  float m[CPL][8];
 #pragma unroll
-  for (int t = 0; t < 8; ++t) m[t] = 0.f;
+  for (int k = 0; k < CPL; ++k)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) m[k][t] = 0.f;
 
   for (int base = 0; base < cnt; base += RW_STAGES) {
     const unsigned parity = (unsigned)(base / RW_STAGES) & 1u;
@@ -203,51 +255,73 @@ __global__ void __launch_bounds__(32 * K)
     for (int s = 0; s < RW_STAGES; ++s) {
       const int i = base + s;
       if (i < cnt) {
-        const unsigned stg = stages + (unsigned)(s * RW_STAGE_BYTES);
+        const unsigned stg = stages + (unsigned)(s * STAGE);
         mbar_wait(bars + 8u * s, parity);
         const int n = en[s];
         const float w = ew[s];
-        const float4 ga = lds_v4(stg + g_lo), gb = lds_v4(stg + g_hi);
-        if (n != cur) {
-          if (cur & 1) rw_flush_jump(st, m); else rw_flush_chain(st, m);
+        float4 ga[CPL], gb[CPL];
 #pragma unroll
-          for (int t = 0; t < 8; ++t) m[t] = 0.f;
-          if (n & 1) rw_load_cols<true>(st, stg + RW_TILE_BYTES, row_addr);
-          else rw_load_cols<false>(st, stg + RW_TILE_BYTES, row_addr);
+        for (int k = 0; k < CPL; ++k) {
+          ga[k] = lds_v4(stg + g_lo + 1024u * k);
+          gb[k] = lds_v4(stg + g_hi + 1024u * k);
+        }
+        if (n != cur) {
+          if (cur & 1) rw_flush_jump<CPL>(st, m); else rw_flush_chain<CPL>(st, m);
+#pragma unroll
+          for (int k = 0; k < CPL; ++k)
+#pragma unroll
+            for (int t = 0; t < 8; ++t) m[k][t] = 0.f;
+          if (n & 1) rw_load_cols<true, CPL>(st, stg + TILE, row_addr);
+          else rw_load_cols<false, CPL>(st, stg + TILE, row_addr);
           cur = n;
         }
-        m[0] = fmaf(w, ga.x, m[0]); m[1] = fmaf(w, ga.y, m[1]); m[2] = fmaf(w, ga.z, m[2]); m[3] = fmaf(w, ga.w, m[3]);
-        m[4] = fmaf(w, gb.x, m[4]); m[5] = fmaf(w, gb.y, m[5]); m[6] = fmaf(w, gb.z, m[6]); m[7] = fmaf(w, gb.w, m[7]);
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+          m[k][0] = fmaf(w, ga[k].x, m[k][0]); m[k][1] = fmaf(w, ga[k].y, m[k][1]);
+          m[k][2] = fmaf(w, ga[k].z, m[k][2]); m[k][3] = fmaf(w, ga[k].w, m[k][3]);
+          m[k][4] = fmaf(w, gb[k].x, m[k][4]); m[k][5] = fmaf(w, gb[k].y, m[k][5]);
+          m[k][6] = fmaf(w, gb[k].z, m[k][6]); m[k][7] = fmaf(w, gb[k].w, m[k][7]);
+        }
         // the stage has been read (the sums above depend on it): refill it
         __syncwarp();
         if (i + RW_STAGES < cnt) issue(i + RW_STAGES, s);
       }
     }
   }
-  if (cur & 1) rw_flush_jump(st, m); else rw_flush_chain(st, m);
+  if (cur & 1) rw_flush_jump<CPL>(st, m); else rw_flush_chain<CPL>(st, m);
   if (K > 1) __syncthreads(); else __syncwarp();
 
-  // ---- write the row: warp k takes channels k, k + K, ...; lanes along the cells ----
+  // ---- write the row: lanes along the cells; warp k takes lane-rows k, k + K, ... ----
   float* out = bottom_grad + (((size_t)img * C + c0) * H + y) * W;
   const size_t plane = (size_t)H * W;
-  const float* row0 = reinterpret_cast<const float*>(smem_rw + RW_STAGES * RW_STAGE_BYTES);
-  const unsigned wstride = rw_warp_bytes(Ws, RW_STAGES) / 4u;
-  for (int ch = wid; ch < 32; ch += K)
-    for (int x = lane; x < W; x += 32) {
-      float v = row0[ch * Ws + x];
+  if (CPL == 1) {
+    const float* row0 = reinterpret_cast<const float*>(smem_rw + RW_STAGES * STAGE);
+    const unsigned wstride = rw_warp_bytes(Ws, CPL) / 4u;
+    for (int ch = wid; ch < 32; ch += K)
+      for (int x = lane; x < W; x += 32) {
+        float v = row0[ch * Ws + x];
 #pragma unroll
-      for (int k = 1; k < K; ++k) v += row0[k * wstride + ch * Ws + x];
-      out[ch * plane + x] = v;
-    }
+        for (int k = 1; k < K; ++k) v += row0[k * wstride + ch * Ws + x];
+        out[ch * plane + x] = v;
+      }
+  } else {
+    const unsigned row_base = smem_u32(row);
+    for (int ch = 0; ch < 32; ++ch)
+      for (int x = lane; x < W; x += 32) {
+        const float2 v = lds_v2(row_base + 8u * (unsigned)(ch * Ws + x));
+        out[ch * plane + x] = v.x;
+        out[(ch + 32) * plane + x] = v.y;
+      }
+  }
 }
 
-// (R, C, AH, 8) fp32 gradient tensor; box = one 8-wide row of 32 consecutive channels
-static bool make_grad_tmap(CUtensorMap* map, const float* top_grad, int R, int C, int AH) {
+// (R, C, AH, 8) fp32 gradient tensor; box = one 8-wide row of `box_ch` consecutive channels
+static bool make_grad_tmap(CUtensorMap* map, const float* top_grad, int R, int C, int AH, int box_ch) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return false;
   const cuuint64_t dims[4] = {8, (cuuint64_t)AH, (cuuint64_t)C, (cuuint64_t)R};
   const cuuint64_t strides[3] = {32, (cuuint64_t)AH * 32, (cuuint64_t)C * AH * 32};
-  const cuuint32_t box[4] = {8, 1, 32, 1};
+  const cuuint32_t box[4] = {8, 1, (cuuint32_t)box_ch, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(top_grad), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -277,25 +351,29 @@ extern "C" int tlod_roi_align_backward(const float* top_grad, const float* rois,
   if (planned && plan_has_row_lists(batch, height) && channels % 32 == 0 && aligned_w == 8 &&
       ((uintptr_t)top_grad & 15) == 0) {
     const int Ws = (width + 1) | 1;  // + dump cell; odd stride: lane = channel is conflict free
-    const long long grid = (long long)batch * height * (channels / 32);
+    const int sms = device_info().sm_count;
+    const size_t smem_max = (size_t)device_info().max_smem_optin;
+    // two channels per lane when that still leaves at least two waves of one-warp CTAs
+    const long long grid2 = (long long)batch * height * (channels / 64);
+    const long long slots2 = (long long)sms * ((227 * 1024) / (rw_warp_bytes(Ws, 2) + 1024));
+    const int cpl = (channels % 64 == 0 && rw_warp_bytes(Ws, 2) <= smem_max && slots2 > 0 && grid2 >= 2 * slots2) ? 2 : 1;
+    const long long grid = (long long)batch * height * (channels / (32 * cpl));
     // small grids: K warps per row until ~12 warps per SM are in flight
     int K = 1;
-    while (K < 4 && grid * K < 12LL * device_info().sm_count &&
-           (size_t)(K + 1) * rw_warp_bytes(Ws, RW_STAGES) <= (size_t)device_info().max_smem_optin)
-      ++K;
-    const size_t smem = (size_t)K * rw_warp_bytes(Ws, RW_STAGES);
+    while (cpl == 1 && K < 4 && grid * K < 12LL * sms && (size_t)(K + 1) * rw_warp_bytes(Ws, 1) <= smem_max) ++K;
+    const size_t smem = (size_t)K * rw_warp_bytes(Ws, cpl);
     CUtensorMap tmap;
-    if (grid <= 2147483647LL && smem <= (size_t)device_info().max_smem_optin &&
-        make_grad_tmap(&tmap, top_grad, num_rois, channels, aligned_h)) {
-      auto kern = K == 1 ? roi_align_bwd_rows_kernel<1> : K == 2 ? roi_align_bwd_rows_kernel<2>
-                  : K == 3 ? roi_align_bwd_rows_kernel<3> : roi_align_bwd_rows_kernel<4>;
+    if (grid <= 2147483647LL && smem <= smem_max &&
+        make_grad_tmap(&tmap, top_grad, num_rois, channels, aligned_h, 32 * cpl)) {
+      auto kern = cpl == 2 ? roi_align_bwd_rows_kernel<1, 2>
+                  : K == 1 ? roi_align_bwd_rows_kernel<1, 1> : K == 2 ? roi_align_bwd_rows_kernel<2, 1>
+                  : K == 3 ? roi_align_bwd_rows_kernel<3, 1> : roi_align_bwd_rows_kernel<4, 1>;
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
       const PlanPtrs pl = plan_ptrs(const_cast<void*>(plan), batch, num_rois);
       {
         LaunchScope scope("roi_align_bwd_rows_kernel", st);
-        kern<<<(int)grid, 32 * K, smem, st>>>(tmap, bottom_grad, pl, batch, channels, height,
-                                                              width, Ws);
+        kern<<<(int)grid, 32 * K, smem, st>>>(tmap, bottom_grad, pl, batch, channels, height, width, Ws);
       }
       return last_launch_status();
     }
