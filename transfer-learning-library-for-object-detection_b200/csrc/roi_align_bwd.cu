@@ -27,7 +27,7 @@
 
 namespace tlod {
 
-constexpr int RW_STAGES = 3;  // ring depth per warp (2..4 measure the same; fewer = more warps per SM)
+constexpr int RW_STAGES = 2;  // ring depth per warp (2..4 measure within 3 %; fewer = more warps per SM)
 constexpr int RW_META_BYTES = 256;  // BwdCols (224), padded: keeps the tiles' swizzle phase
 // CPL = channels per lane (1 or 2): a warp owns 32 * CPL channels of its row.  With CPL = 2 a
 // cell holds the pair (channel lane, channel lane + 32) as a float2: one 64-bit shared-memory
