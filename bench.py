@@ -101,6 +101,7 @@ class TlodStep(object):
         self.streams = None
         self.launches_per_replay = 0
         self.host_out = None
+        self.side = None
         if use_graph:
             self.capture()
 
@@ -184,10 +185,17 @@ class TlodStep(object):
 
     def step(self, d=None, copy_in=None, copy_out=None):
         d = self.d if d is None else d
-        # anchor targets: launch the label kernel first (own stream), queue the rest of the step,
-        # then do the host-side subsampling while the GPU works through the queue
-        pending = self.anchor_target.begin((d["src_prob"], d["src_gt"], d["src_im_info"], self.num_boxes))
+        # Queue the two domains first (two graph launches), then start the anchor-target layer on a
+        # side stream that only depends on the step's inputs: its label kernels run beside the
+        # domain graphs, and its host-side subsampling (numpy's RNG stream, like the reference)
+        # runs while the GPU works through the queue.
+        cur = torch.cuda.current_stream(self.dev)
+        if self.side is None:
+            self.side = torch.cuda.Stream(self.dev)
+        self.side.wait_stream(cur)
         results = self.device_part(d, copy_in, copy_out)
+        with torch.cuda.stream(self.side):
+            pending = self.anchor_target.begin((d["src_prob"], d["src_gt"], d["src_im_info"], self.num_boxes))
         results["anchor_targets"] = self.anchor_target.finish(pending)
         return results
 

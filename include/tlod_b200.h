@@ -250,6 +250,19 @@ int tlod_anchor_labels(const float* anchors, const float* gt, int gt_stride, flo
                        int* argmax, float* max_overlaps, int batch, int n, int k,
                        float negative_overlap, float positive_overlap, int clobber_positives,
                        void* workspace, size_t workspace_bytes, void* stream);
+/* HOST function (no device work): the random subsampling between the two kernels,
+ * lib/model/rpn/anchor_target_layer.py:118-145, on the host copy of labels (batch, n) in
+ * {-1, 0, 1}, edited in place: per image, surplus foreground labels beyond num_fg and surplus
+ * background labels beyond rpn_batchsize - (foreground kept) are set to -1, chosen with
+ * np.random.permutation exactly as the reference does.  mt_key (624 words) / mt_pos are numpy's
+ * global MT19937 state (np.random.get_state()[1:3]); they are advanced in place, to be put back
+ * with np.random.set_state(), so the stream continues as after the reference's own calls.
+ * num_examples_last = number of labels >= 0 of the LAST image (:156, stale loop variable). */
+int tlod_anchor_subsample_host(float* labels, int batch, int n, int num_fg, int rpn_batchsize,
+                               unsigned int* mt_key, int* mt_pos, int* num_examples_last);
+/* HOST function: out[0..n) = np.random.permutation(n) drawn from the given MT19937 state
+ * (numpy's legacy RandomState: Fisher-Yates from the top, masked rejection sampling). */
+int tlod_numpy_permutation(unsigned int* mt_key, int* mt_pos, long long n, long long* out);
 /* Final maps.  labels/argmax (batch, n) over inside anchors (after the host
  * subsampling); inv_index (total) int32: position of each of the total = H*W*A
  * anchors in the inside list or -1.

@@ -53,6 +53,9 @@ SIGNATURES = {
     "tlod_anchor_labels_workspace_bytes": (c_size_t, [c_int, c_int]),
     "tlod_anchor_labels": (c_int, [P, P, c_int, P, P, P, c_int, c_int, c_int, c_float, c_float, c_int,
                                    P, c_size_t, P]),
+    "tlod_anchor_subsample_host": (c_int, [P, c_int, c_int, c_int, c_int, P, ctypes.POINTER(c_int),
+                                           ctypes.POINTER(c_int)]),
+    "tlod_numpy_permutation": (c_int, [P, ctypes.POINTER(c_int), c_longlong, P]),
     "tlod_anchor_targets_finalize": (c_int, [P, P, P, P, c_int, P, P, P, P, P, c_int, c_int, c_int, c_int,
                                              c_int, c_int, c_float, c_float, c_float, P]),
     "tlod_roi_gt_assign": (c_int, [P, c_int, c_int, P, c_int, P, P, P, c_int, c_int, c_int, P]),
