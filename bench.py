@@ -592,7 +592,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cfg3", action="store_true", help="skip the cfg3-scale RoIAlign roofline section")
     ap.add_argument("--no-graph", action="store_true", help="run the device part eagerly instead of a CUDA graph")
+    ap.add_argument("--watchdog", type=int, default=1500,
+                    help="seconds after which a stuck run dumps its Python stacks and exits (0 = off)")
     args = ap.parse_args()
+    if args.watchdog > 0:
+        import faulthandler
+        faulthandler.dump_traceback_later(args.watchdog, exit=True, file=sys.stderr)
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
