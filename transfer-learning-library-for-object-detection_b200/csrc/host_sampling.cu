@@ -92,15 +92,39 @@ void legacy_permutation(Mt19937& rng, T* x, long long n) {
   uint32_t i = (uint32_t)(n - 1);
   uint32_t mask = i;
   mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+  // draws are consumed from a block of tempered words (the tempering vectorises); rng.pos is the
+  // position inside numpy's key array, as numpy keeps it
+  uint32_t block[624];
+  int avail = 0, at = 0;
   while (i >= 1) {
-    if (i <= (mask >> 1)) mask >>= 1;  // log2(n) times
-    const uint32_t v = rng.next32() & mask;
-    const uint32_t acc = v <= i;
-    const uint32_t j = acc ? v : i;
-    const T a = x[i], b = x[j];
-    x[i] = b;
-    x[j] = a;
-    i -= acc;
+    if (at == avail) {
+      if (rng.pos == 624) rng.refill();
+      avail = 624 - rng.pos;
+      const uint32_t* k = rng.key + rng.pos;
+      for (int q = 0; q < avail; ++q) {
+        uint32_t y = k[q];
+        y ^= (y >> 11);
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= (y >> 18);
+        block[q] = y;
+      }
+      at = 0;
+    }
+    // consume until the block runs out or the permutation is complete
+    int q = at;
+    while (q < avail && i >= 1) {
+      if (i <= (mask >> 1)) mask >>= 1;  // log2(n) times
+      const uint32_t v = block[q++] & mask;
+      const uint32_t acc = v <= i;
+      const uint32_t j = acc ? v : i;
+      const T a = x[i], b = x[j];
+      x[i] = b;
+      x[j] = a;
+      i -= acc;
+    }
+    rng.pos += q - at;
+    at = q;
   }
 }
 
@@ -122,14 +146,22 @@ extern "C" int tlod_anchor_subsample_host(float* labels, int batch, int n, int n
   Mt19937 rng{mt_key, *mt_pos};
   std::vector<int> fg, bg, perm;
   fg.reserve(n);
-  bg.reserve(n);
+  bg.resize(n);
   perm.reserve(n);
   int examples = 0;
   for (int i = 0; i < batch; ++i) {
     float* lab = labels + (size_t)i * n;
+    // one pass: the foreground subsampling only turns 1 into -1, so the background list
+    // (labels == 0) can be collected before it
     fg.clear();
-    for (int k = 0; k < n; ++k)
-      if (lab[k] == 1.f) fg.push_back(k);
+    int n_bg = 0;
+    int* bgp = bg.data();
+    for (int k = 0; k < n; ++k) {
+      const float v = lab[k];
+      bgp[n_bg] = k;
+      n_bg += v == 0.f;
+      if (v == 1.f) fg.push_back(k);
+    }
     int n_fg = (int)fg.size();
     if (n_fg > num_fg) {  // :124-132
       perm.resize(n_fg);
@@ -138,19 +170,15 @@ extern "C" int tlod_anchor_subsample_host(float* labels, int batch, int n, int n
       n_fg = num_fg;
     }
     const int num_bg = rpn_batchsize - n_fg;  // :135
-    bg.clear();
-    for (int k = 0; k < n; ++k)
-      if (lab[k] == 0.f) bg.push_back(k);
-    const int n_bg = (int)bg.size();
+    int bg_kept = n_bg;
     if (n_bg > num_bg) {  // :138-145
       perm.resize(n_bg);
       legacy_permutation(rng, perm.data(), n_bg);
-      for (int k = 0; k < n_bg - num_bg; ++k) lab[bg[perm[k]]] = -1.f;
+      for (int k = 0; k < n_bg - num_bg; ++k) lab[bgp[perm[k]]] = -1.f;
+      bg_kept = num_bg > 0 ? num_bg : 0;
     }
-    if (i == batch - 1) {  // :156 -- the LAST image's count (stale loop variable in the reference)
-      examples = 0;
-      for (int k = 0; k < n; ++k) examples += lab[k] >= 0.f;
-    }
+    // :156 -- the LAST image's count of labels >= 0 (stale loop variable in the reference)
+    examples = n_fg + bg_kept;
   }
   *mt_pos = rng.pos;
   *num_examples_last = examples;
