@@ -169,7 +169,6 @@ template <int K, int CPL>
 __global__ void __launch_bounds__(32 * K)
     roi_align_bwd_rows_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ bottom_grad,
                               PlanPtrs pl, int B, int C, int H, int W, int Ws) {
-  static_assert(CPL == 1 || (CPL == 2 && K == 1), "two channels per lane: one warp per row");
   constexpr int TILE = rw_tile_bytes(CPL), STAGE = rw_stage_bytes(CPL), CH = 32 * CPL;
   extern __shared__ __align__(1024) unsigned char smem_rw[];
   const int lane = lane_id(), wid = K > 1 ? warp_id() : 0;
@@ -305,10 +304,17 @@ __global__ void __launch_bounds__(32 * K)
         out[ch * plane + x] = v;
       }
   } else {
-    const unsigned row_base = smem_u32(row);
-    for (int ch = 0; ch < 32; ++ch)
+    const unsigned row_base = smem_u32(smem_rw + RW_STAGES * STAGE);
+    const unsigned wbytes = rw_warp_bytes(Ws, CPL);
+    for (int ch = wid; ch < 32; ch += K)
       for (int x = lane; x < W; x += 32) {
-        const float2 v = lds_v2(row_base + 8u * (unsigned)(ch * Ws + x));
+        float2 v = lds_v2(row_base + 8u * (unsigned)(ch * Ws + x));
+#pragma unroll
+        for (int k = 1; k < K; ++k) {
+          const float2 t = lds_v2(row_base + (unsigned)k * wbytes + 8u * (unsigned)(ch * Ws + x));
+          v.x += t.x;
+          v.y += t.y;
+        }
         out[ch * plane + x] = v.x;
         out[(ch + 32) * plane + x] = v.y;
       }
@@ -353,21 +359,26 @@ extern "C" int tlod_roi_align_backward(const float* top_grad, const float* rois,
     const int Ws = (width + 1) | 1;  // + dump cell; odd stride: lane = channel is conflict free
     const int sms = device_info().sm_count;
     const size_t smem_max = (size_t)device_info().max_smem_optin;
-    // two channels per lane when that still leaves at least two waves of one-warp CTAs
-    const long long grid2 = (long long)batch * height * (channels / 64);
-    const long long slots2 = (long long)sms * ((227 * 1024) / (rw_warp_bytes(Ws, 2) + 1024));
-    const int cpl = (channels % 64 == 0 && rw_warp_bytes(Ws, 2) <= smem_max && slots2 > 0 && grid2 >= 2 * slots2) ? 2 : 1;
+    // Two channels per lane (half the instructions per channel, twice the shared memory per warp)
+    // whenever channels % 64 == 0; K warps per row on grids that would leave SMs idle.
+    int cpl = 1, K = 1;
+    if (channels % 64 == 0 && rw_warp_bytes(Ws, 2) <= smem_max) {
+      cpl = 2;
+      const long long grid2 = (long long)batch * height * (channels / 64);
+      while (K < 4 && grid2 * K < 6LL * sms && (size_t)(K + 1) * rw_warp_bytes(Ws, 2) <= smem_max) ++K;
+    } else {
+      const long long grid1 = (long long)batch * height * (channels / 32);
+      while (K < 4 && grid1 * K < 12LL * sms && (size_t)(K + 1) * rw_warp_bytes(Ws, 1) <= smem_max) ++K;
+    }
     const long long grid = (long long)batch * height * (channels / (32 * cpl));
-    // small grids: K warps per row until ~12 warps per SM are in flight
-    int K = 1;
-    while (cpl == 1 && K < 4 && grid * K < 12LL * sms && (size_t)(K + 1) * rw_warp_bytes(Ws, 1) <= smem_max) ++K;
     const size_t smem = (size_t)K * rw_warp_bytes(Ws, cpl);
     CUtensorMap tmap;
     if (grid <= 2147483647LL && smem <= smem_max &&
         make_grad_tmap(&tmap, top_grad, num_rois, channels, aligned_h, 32 * cpl)) {
-      auto kern = cpl == 2 ? roi_align_bwd_rows_kernel<1, 2>
-                  : K == 1 ? roi_align_bwd_rows_kernel<1, 1> : K == 2 ? roi_align_bwd_rows_kernel<2, 1>
-                  : K == 3 ? roi_align_bwd_rows_kernel<3, 1> : roi_align_bwd_rows_kernel<4, 1>;
+      auto kern = cpl == 2 ? (K == 1 ? roi_align_bwd_rows_kernel<1, 2> : K == 2 ? roi_align_bwd_rows_kernel<2, 2>
+                              : K == 3 ? roi_align_bwd_rows_kernel<3, 2> : roi_align_bwd_rows_kernel<4, 2>)
+                           : (K == 1 ? roi_align_bwd_rows_kernel<1, 1> : K == 2 ? roi_align_bwd_rows_kernel<2, 1>
+                              : K == 3 ? roi_align_bwd_rows_kernel<3, 1> : roi_align_bwd_rows_kernel<4, 1>);
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
       const PlanPtrs pl = plan_ptrs(const_cast<void*>(plan), batch, num_rois);
