@@ -323,6 +323,92 @@ def roi_align_cfg3(dev, iters=20):
     return out
 
 
+def secondary_metrics(dev, iters=20):
+    """The other metrics SURVEY 8(d) names, measured alone on rank 0: the two proposal pipelines
+    (12000 -> 2000 TRAIN, 6000 -> 300 TEST; proposal sets/s, proposals/s, fraction of the bound
+    8(d) defines: max(bytes / HBM rate, 16 flop per upper-triangle pair / fp32 SIMT rate)), the
+    cfg5 NMS sweep (batch x IoU threshold) and RoIPool forward + backward."""
+    from oracle.synth import synth_rois, synth_rpn
+    from model.rpn.generate_anchors import generate_anchors
+    from tlod_b200 import functional as F
+    peak, _ = peaks()
+    fp32_tflops = 148 * 128 * 2 * 1.965e9 / 1e12  # nominal SIMT rate (SURVEY 8d)
+
+    def per_call_us(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters * 1e3
+
+    anchors = torch.from_numpy(generate_anchors(scales=np.array([4, 8, 16, 32]),
+                                                ratios=np.array([0.5, 1, 2]))).float().to(dev)
+    out = {"fp32_simt_tflops_nominal": fp32_tflops, "proposal_layer": {}, "nms_sweep_test_6000_300": []}
+    inputs = {}
+
+    def rpn(batch):
+        if batch not in inputs:
+            prob, deltas = synth_rpn(batch, A, H, W, 3)
+            info = torch.tensor([[600.0, 1200.0, 0.5859375]] * batch)
+            inputs[batch] = [t.to(dev) for t in (prob, deltas, info)]
+        return inputs[batch]
+
+    for name, pre, post in (("TRAIN_12000_2000", 12000, 2000), ("TEST_6000_300", 6000, 300)):
+        prob, deltas, info = rpn(2)
+        us = per_call_us(lambda: F.proposals(prob, deltas, info, anchors, 16, pre, post, 0.7))
+        nbytes = 2 * (A * H * W * 4 * 5 + post * 20)
+        flops = 2 * (pre * (pre - 1) / 2) * 16
+        bound_us = max(nbytes / (peak * 1e9), flops / (fp32_tflops * 1e12)) * 1e6
+        out["proposal_layer"][name] = {"images": 2, "us_per_call": us, "proposal_sets_per_s": 2 / (us * 1e-6),
+                                       "proposals_per_s": 2 * post / (us * 1e-6), "bound_us": bound_us,
+                                       "frac_of_bound": bound_us / us,
+                                       "note": "bound = full upper-triangle IoU work on the nominal fp32 SIMT "
+                                               "rate; the phased NMS computes only the triangle the scan reaches"}
+    for batch in (1, 8, 64):
+        prob, deltas, info = rpn(batch)
+        for thr in (0.3, 0.5, 0.7):
+            us = per_call_us(lambda: F.proposals(prob, deltas, info, anchors, 16, 6000, 300, thr))
+            out["nms_sweep_test_6000_300"].append({"batch": batch, "iou": thr, "us_per_call": us,
+                                                   "proposal_sets_per_s": batch / (us * 1e-6)})
+    # RoIPool 7x7 forward + backward at cfg1 / cfg2 scale (VGG16 conv5, 2 images, 512 RoIs)
+    g = torch.Generator().manual_seed(5)
+    feat = torch.relu(torch.randn(2, C, H, W, generator=g)).to(dev)
+    rois = synth_rois(512, 2, 41).to(dev)
+    top = torch.randn(512, C, 7, 7, device=dev)
+    pooled, argmax = F.roi_pool_forward(feat, rois, 7, 7, 1.0 / 16)
+    us_f = per_call_us(lambda: F.roi_pool_forward(feat, rois, 7, 7, 1.0 / 16))
+    us_b = per_call_us(lambda: F.roi_pool_backward(top, argmax, rois, feat.shape, 1.0 / 16))
+    alg_f = feat.numel() * 4 + 512 * 20 + 512 * C * 49 * 8
+    out["roi_pool_2x512x37x75_512rois"] = {
+        "fwd_us": us_f, "bwd_us": us_b, "rois_per_s_fwd_bwd": 512 / ((us_f + us_b) * 1e-6),
+        "frac_of_hbm_peak_fwd": alg_f / (us_f * 1e-6) / 1e9 / peak,
+        "frac_of_hbm_peak_bwd": alg_f / (us_b * 1e-6) / 1e9 / peak,
+        "note": "L2-warm back-to-back launches (working set 63 MB < L2)"}
+    # BASELINE cfg3 (ii): the crop path -- RoICrop 14x14 on conv4 (8, 1024, 38, 75), 2048 RoIs
+    from model.utils.net_utils import _affine_grid_gen
+    Bc, Cc, Hc, Wc, Rc, G = 8, 1024, 38, 75, 2048, 14
+    featc = torch.relu(torch.randn(Bc, Cc, Hc, Wc, generator=g)).to(dev)
+    roisc = synth_rois(Rc, Bc, 41)
+    roisc = roisc[torch.argsort(roisc[:, 0], stable=True)].contiguous().to(dev)
+    grid_xy = _affine_grid_gen(roisc, (Hc, Wc), G)
+    grid_yx = torch.stack([grid_xy[..., 1], grid_xy[..., 0]], 3).contiguous()
+    topc = torch.randn(Rc, Cc, G, G, device=dev)
+    us_cf = per_call_us(lambda: F.roi_crop_forward(featc, grid_yx))
+    us_cb = per_call_us(lambda: F.roi_crop_backward(topc, grid_yx, featc.shape))
+    alg_c = featc.numel() * 4 + grid_yx.numel() * 4 + Rc * Cc * G * G * 4
+    out["roi_crop_cfg3_14x14"] = {
+        "fwd_us": us_cf, "bwd_us": us_cb, "rois_per_s_fwd_bwd": Rc / ((us_cf + us_cb) * 1e-6),
+        "algorithmic_bytes_per_direction": alg_c,
+        "frac_of_hbm_peak_fwd": alg_c / (us_cf * 1e-6) / 1e9 / peak,
+        "frac_of_hbm_peak_bwd": alg_c / (us_cb * 1e-6) / 1e9 / peak}
+    return out
+
+
 def run_tlod(args):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -412,8 +498,10 @@ def run_tlod(args):
     # HBM-bound evidence: RoIAlign forward / backward alone at cfg3 scale (8x1024x38x75, 2048 RoIs,
     # 630 MB of algorithmic traffic per direction: larger than L2, so no flush is needed)
     cfg3 = None
+    secondary = None
     if rank == 0 and not args.no_cfg3:
         cfg3 = roi_align_cfg3(dev)
+        secondary = secondary_metrics(dev)
 
     if rank != 0:
         if world > 1:
@@ -485,7 +573,7 @@ def run_tlod(args):
         "cuda_graph": step.graph is not None,
         "clocks": parse_clocks(clock_file),
         "roofline": roofline, "roofline_by_kernel": by_kernel,
-        "dominant_kernel": dominant, "kernels": kernels, "roi_align_cfg3": cfg3,
+        "dominant_kernel": dominant, "kernels": kernels, "roi_align_cfg3": cfg3, "secondary": secondary,
         "wall_s": wall,
     }
     if not args.no_cpu_baseline:
