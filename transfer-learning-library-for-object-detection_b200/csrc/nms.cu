@@ -223,8 +223,9 @@ __device__ __forceinline__ unsigned long long resolve_chunk(unsigned long long c
 //     remv[c]                      rows of survivors of chunks <= c-3   (other warps, below)
 //   | OR survivors(c-1) of mask[row][c]   "s1", prefetched by warp 0 before it knew the survivors
 //   | OR survivors(c-2) of mask[row][c]   "s2", likewise
-// The other 7 warps fold the rows of chunk c's survivors into remv[j >= c+3]; their loads are
-// issued in iteration c and consumed in iteration c+1, two barriers before warp 0 needs them.
+// The other 7 warps fold the rows of chunk c's survivors into remv[j >= c+3]: their loads are
+// issued in iteration c and OR-ed into lane-private partial words in iteration c+1; word j is
+// reduced across the lanes once, in iteration j-2, two barriers before warp 0 needs it.
 __global__ void __launch_bounds__(SCAN_THREADS)
     nms_scan_kernel(const unsigned long long* __restrict__ mask, int n, int max_keep,
                     int* __restrict__ keep_out, int keep_stride, int* __restrict__ num_out,
@@ -272,6 +273,9 @@ __global__ void __launch_bounds__(SCAN_THREADS)
   constexpr int HW = SCAN_THREADS / 32 - 1;  // helper warps
   constexpr int MAXG = 4;                    // word groups per helper warp kept in flight
   ulonglong4 pend[MAXG][2];
+  ulonglong4 acc[MAXG];  // lane-private OR of the rows folded so far, per owned word group
+#pragma unroll
+  for (int u = 0; u < MAXG; ++u) acc[u] = make_ulonglong4(0ULL, 0ULL, 0ULL, 0ULL);
   int pend_c = -1;
   for (int c = c0; c < c1; ++c) {
     if (wid == 0) {
@@ -322,49 +326,57 @@ __global__ void __launch_bounds__(SCAN_THREADS)
     if (done_sh[c & 1]) break;
     if (wid != 0) {
       const int h = wid - 1;
-      // fold the sectors loaded one iteration ago (rows of chunk pend_c's survivors)
+      const int gbase = c0 >> 2;  // helper h owns the word groups gbase + h + u * HW, u < MAXG
+      // 1. the sectors loaded one iteration ago (rows of chunk c-1's survivors) join the lane's
+      //    private partial ORs: no cross-lane reduction here (REDUX is the scarce resource: the
+      //    per-chunk reduction of every word took 224 of them per iteration)
       if (pend_c >= 0) {
-        const int g0 = (pend_c + 3) >> 2;  // first word group with words >= pend_c + 3
 #pragma unroll
         for (int u = 0; u < MAXG; ++u) {
-          const int g = g0 + h + u * HW;
-          if (4 * g < c1) {
-            const unsigned long long w0 = warp_or_u64(pend[u][0].x | pend[u][1].x);
-            const unsigned long long w1 = warp_or_u64(pend[u][0].y | pend[u][1].y);
-            const unsigned long long w2 = warp_or_u64(pend[u][0].z | pend[u][1].z);
-            const unsigned long long w3 = warp_or_u64(pend[u][0].w | pend[u][1].w);
-            if (lane == 0) {
-              // words below pend_c + 3 are covered by warp 0's s1 / s2 path or already passed
-              if (4 * g + 0 >= pend_c + 3 && 4 * g + 0 < c1) remv[4 * g + 0] |= w0;
-              if (4 * g + 1 >= pend_c + 3 && 4 * g + 1 < c1) remv[4 * g + 1] |= w1;
-              if (4 * g + 2 >= pend_c + 3 && 4 * g + 2 < c1) remv[4 * g + 2] |= w2;
-              if (4 * g + 3 >= pend_c + 3 && 4 * g + 3 < c1) remv[4 * g + 3] |= w3;
-            }
-          }
+          acc[u].x |= pend[u][0].x | pend[u][1].x;
+          acc[u].y |= pend[u][0].y | pend[u][1].y;
+          acc[u].z |= pend[u][0].z | pend[u][1].z;
+          acc[u].w |= pend[u][0].w | pend[u][1].w;
         }
         pend_c = -1;
       }
-      // rows of chunk c's survivors -> words [c+3, c1)
+      // 2. word c + 2 now holds the survivors of every chunk <= c - 1 (those of chunks c, c + 1
+      //    reach it through warp 0's s1 / s2 path): reduce it across the lanes, once, two
+      //    barriers before warp 0 reads it
+      {
+        const int j = c + 2;
+        const int gj = (j >> 2) - gbase;
+        if (j < c1 && gj % HW == h && gj / HW < MAXG) {
+          const int uo = gj / HW, qo = j & 3;
+          unsigned long long v = 0ULL;
+#pragma unroll
+          for (int u = 0; u < MAXG; ++u)
+            if (u == uo) v = qo == 0 ? acc[u].x : qo == 1 ? acc[u].y : qo == 2 ? acc[u].z : acc[u].w;
+          v = warp_or_u64(v);
+          if (lane == 0) remv[j] |= v;
+        }
+      }
+      // 3. rows of chunk c's survivors -> words [c+3, c1)
       const unsigned long long k = kept_sh[c & 1];
       if (k && c + 3 < c1) {
-        const int g0 = (c + 3) >> 2;
         const bool s0 = (k >> lane) & 1ULL, s1 = (k >> (lane + 32)) & 1ULL;
         const ulonglong4 zero = make_ulonglong4(0ULL, 0ULL, 0ULL, 0ULL);
         const unsigned long long* r0 = m + (size_t)(64 * c + lane) * rs;
         const unsigned long long* r1 = m + (size_t)(64 * c + lane + 32) * rs;
 #pragma unroll
         for (int u = 0; u < MAXG; ++u) {
-          const int g = g0 + h + u * HW;
+          const int g = gbase + h + u * HW;
           pend[u][0] = zero;
           pend[u][1] = zero;
-          if (4 * g < c1) {
+          if (4 * g < c1 && 4 * g + 3 >= c + 3) {
             if (s0) pend[u][0] = *reinterpret_cast<const ulonglong4*>(r0 + 4 * g);
             if (s1) pend[u][1] = *reinterpret_cast<const ulonglong4*>(r1 + 4 * g);
           }
         }
         pend_c = c;
-        // phases wider than MAXG * HW * 4 = 112 words: the rest, folded at once
-        for (int g = g0 + h + MAXG * HW; 4 * g < c1; g += HW) {
+        // phases wider than MAXG * HW * 4 = 112 words: the rest, reduced per chunk
+        for (int g = gbase + h + MAXG * HW; 4 * g < c1; g += HW) {
+          if (4 * g + 3 < c + 3) continue;
           unsigned long long w[4] = {0ULL, 0ULL, 0ULL, 0ULL};
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
