@@ -86,7 +86,8 @@ __host__ __device__ inline int nms_phase_end(int n, int max_keep, int phase /* 1
 // Persistent grid (gridDim.x CTAs per image, blockIdx.y = image); 256 threads: thread t owns
 // row t >> 2 of a 64x64 tile and 16 of its 64 columns.  The tiles of a phase are the pairs
 // (col block cb in [cb0, cb1), row block rb <= cb), numbered cb-major.
-// mask[(img * n + row) * ncb + col_block], bits for columns > row only.
+// mask[(img * n + row) * rs + col_block]; in the diagonal tile the word holds every other box of
+// the chunk that overlaps the row's box (both directions).
 template <bool FILTER>
 __global__ void __launch_bounds__(256)
     nms_mask_kernel(const float* __restrict__ boxes, int n, int stride, float thresh,
@@ -143,7 +144,9 @@ __global__ void __launch_bounds__(256)
     lo |= __shfl_xor_sync(0xffffffffu, lo, 2); hi |= __shfl_xor_sync(0xffffffffu, hi, 2);
     if (q == 0 && r < row_size) {
       unsigned long long w = ((unsigned long long)hi << 32) | lo;
-      if (row_blk == col_blk) w &= ~((2ULL << r) - 1ULL);  // keep columns > row only
+      // diagonal tile: the full symmetric word minus the box itself (IoU is symmetric bit for
+      // bit: commutative adds, min / max); the scan derives "earlier boxes that overlap me" from it
+      if (row_blk == col_blk) w &= ~(1ULL << r);
       mask[((size_t)img * n + row) * rs + col_blk] = w;
     }
   }
@@ -190,25 +193,30 @@ __device__ __forceinline__ unsigned long long or_rows(const unsigned long long* 
 }
 
 // Greedy resolve of one 64-box chunk inside a warp.  `cand` = boxes not suppressed from
-// outside the chunk; d0 / d1 = this lane's rows (lane, lane + 32) of the diagonal block
-// (bits above the row index only).  Instead of one step per survivor, every round keeps ALL
-// undecided boxes that no earlier undecided box suppresses (the lowest one always
-// qualifies) and removes their victims; the result equals the sequential scan
-// (nms_cuda_kernel.cu:132-144) and the number of rounds is the longest suppression chain.
+// outside the chunk; f0 / f1 = this lane's words (boxes lane, lane + 32) of the diagonal block:
+// every other box of the chunk that overlaps it.  Only the EARLIER overlappers matter to a box, so
+// all tests are lane-local and a round costs four ballots (the first version reduced row words
+// across the lanes: four REDUX per round, 900 cycles per chunk).  Every round keeps ALL undecided
+// boxes that no earlier undecided box overlaps (the lowest one always qualifies) and removes the
+// boxes they overlap; the result equals the sequential scan (nms_cuda_kernel.cu:132-144) and the
+// number of rounds is the longest suppression chain.
+__device__ __forceinline__ unsigned long long ballot_u64(bool p0, bool p1) {
+  const unsigned lo = __ballot_sync(0xffffffffu, p0), hi = __ballot_sync(0xffffffffu, p1);
+  return ((unsigned long long)hi << 32) | lo;
+}
 __device__ __forceinline__ unsigned long long resolve_chunk(unsigned long long cand,
-                                                            unsigned long long d0,
-                                                            unsigned long long d1, int lane) {
+                                                            unsigned long long f0,
+                                                            unsigned long long f1, int lane) {
+  const unsigned long long low0 = f0 & ((1ULL << lane) - 1ULL);
+  const unsigned long long low1 = f1 & ((1ULL << (lane + 32)) - 1ULL);
   unsigned long long und = cand, kept = 0ULL;
   while (und) {
-    unsigned long long t = 0ULL;
-    if ((und >> lane) & 1ULL) t |= d0;
-    if ((und >> (lane + 32)) & 1ULL) t |= d1;
-    const unsigned long long safe = und & ~warp_or_u64(t);
+    const bool u0 = (und >> lane) & 1ULL, u1 = (und >> (lane + 32)) & 1ULL;
+    const unsigned long long safe = ballot_u64(u0 && !(low0 & und), u1 && !(low1 & und));
     kept |= safe;
-    unsigned long long v = 0ULL;
-    if ((safe >> lane) & 1ULL) v |= d0;
-    if ((safe >> (lane + 32)) & 1ULL) v |= d1;
-    und &= ~(safe | warp_or_u64(v));
+    if (safe == und) break;
+    const unsigned long long victims = ballot_u64(u0 && (low0 & safe), u1 && (low1 & safe));
+    und &= ~(safe | victims);
   }
   return kept;
 }
