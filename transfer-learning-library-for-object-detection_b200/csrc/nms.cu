@@ -84,7 +84,7 @@ __host__ __device__ inline int nms_phase_end(int n, int max_keep, int phase /* 1
 }
 
 // Persistent grid (gridDim.x CTAs per image, blockIdx.y = image); 256 threads: thread t owns
-// row t >> 2 of a 64x64 tile and 16 of its 64 columns.  The tiles of a phase are the pairs
+// row t & 63 of a 64x64 tile and 16 of its 64 columns (quarter t >> 6).  The tiles of a phase are the pairs
 // (col block cb in [cb0, cb1), row block rb <= cb), numbered cb-major.
 // mask[(img * n + row) * rs + col_block]; in the diagonal tile the word holds every other box of
 // the chunk that overlaps the row's box (both directions).
@@ -110,7 +110,10 @@ __global__ void __launch_bounds__(256)
   const float thr_lo = thresh * (1.f - 9.5367431640625e-7f);
   const long long tri0 = (long long)cb0 * (cb0 + 1) / 2;
   const long long ntiles = (long long)cb1 * (cb1 + 1) / 2 - tri0;
-  const int r = t >> 2, q = t & 3;
+  // thread t: row r = t & 63 of the tile, column quarter q = t >> 6 (16 columns).  q is uniform in
+  // a warp, so the column boxes are read as broadcasts (one wavefront per read; with q varying
+  // inside the warp the four quarters sat on the same banks: 4-way conflicts, LSU pipe 80 % busy).
+  const int r = t & 63, q = t >> 6;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     // tile + tri0 = cb (cb + 1) / 2 + rb, 0 <= rb <= cb
     const long long g = tile + tri0;
@@ -137,17 +140,13 @@ __global__ void __launch_bounds__(256)
       if (c < col_size && box_suppresses<FILTER>(a, area_a, cbox[c], carea[c], thresh, thr_hi, thr_lo))
         bits |= 1u << j;
     }
-    // assemble the 64-bit word of the row from its four 16-bit quarters (adjacent lanes)
-    unsigned lo = (q == 0) ? bits : (q == 1 ? bits << 16 : 0u);
-    unsigned hi = (q == 2) ? bits : (q == 3 ? bits << 16 : 0u);
-    lo |= __shfl_xor_sync(0xffffffffu, lo, 1); hi |= __shfl_xor_sync(0xffffffffu, hi, 1);
-    lo |= __shfl_xor_sync(0xffffffffu, lo, 2); hi |= __shfl_xor_sync(0xffffffffu, hi, 2);
-    if (q == 0 && r < row_size) {
-      unsigned long long w = ((unsigned long long)hi << 32) | lo;
+    if (r < row_size) {
       // diagonal tile: the full symmetric word minus the box itself (IoU is symmetric bit for
       // bit: commutative adds, min / max); the scan derives "earlier boxes that overlap me" from it
-      if (row_blk == col_blk) w &= ~(1ULL << r);
-      mask[((size_t)img * n + row) * rs + col_blk] = w;
+      if (row_blk == col_blk && (r >> 4) == q) bits &= ~(1u << (r & 15));
+      // the row's 64-bit word is written as its four 16-bit quarters (little endian)
+      unsigned short* w16 = reinterpret_cast<unsigned short*>(mask + ((size_t)img * n + row) * rs + col_blk);
+      w16[q] = (unsigned short)bits;
     }
   }
 }
