@@ -35,10 +35,13 @@ __device__ __forceinline__ PoolRoi pool_roi(const float* __restrict__ r, float s
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
+// PHT, PWT > 0: compile-time pooled size (7 x 7: the index divisions become multiplications).
+template <int PHT, int PWT>
 __global__ void __launch_bounds__(256)
     roi_pool_fwd_kernel(const float* __restrict__ features, const float* __restrict__ rois,
                         float* __restrict__ output, int* __restrict__ argmax, int B, int C, int H,
-                        int W, int PH, int PW, float scale, int chans_per_block) {
+                        int W, int PH_rt, int PW_rt, float scale, int chans_per_block) {
+  const int PH = PHT > 0 ? PHT : PH_rt, PW = PWT > 0 ? PWT : PW_rt;
   const int n = blockIdx.x;
   const int c0 = blockIdx.y * chans_per_block;
   const PoolRoi g = pool_roi(rois + (size_t)n * 5, scale, PH, PW);
@@ -79,10 +82,12 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+template <int PHT, int PWT>
 __global__ void __launch_bounds__(256)
     roi_pool_bwd_kernel(const float* __restrict__ top_grad, const int* __restrict__ argmax,
                         const float* __restrict__ rois, float* __restrict__ bottom_grad, int B, int C,
-                        int H, int W, int PH, int PW, float scale, int chans_per_block) {
+                        int H, int W, int PH_rt, int PW_rt, float scale, int chans_per_block) {
+  const int PH = PHT > 0 ? PHT : PH_rt, PW = PWT > 0 ? PWT : PW_rt;
   const int n = blockIdx.x;
   const int c0 = blockIdx.y * chans_per_block;
   const PoolRoi g = pool_roi(rois + (size_t)n * 5, scale, PH, PW);
@@ -90,20 +95,21 @@ __global__ void __launch_bounds__(256)
   const int S = PH * PW;
   const int cb = min(chans_per_block, C - c0);
   const size_t roi_base = ((size_t)n * C + c0) * S;
-  const int total = B * C * H * W;
+  const int HW = H * W;
+  const int total = B * C * HW;
   for (int o = threadIdx.x; o < cb * S; o += blockDim.x) {
     const int idx = __ldg(argmax + roi_base + o);
     if (idx < 0 || idx >= total) continue;
     const int c = c0 + o / S;
     const int i = o % S;
     const int ph = i / PW, pw = i - ph * PW;
-    // decode the cell: the reference's thread for cell `idx` only looks at RoIs of
-    // its own image (:150) and at argmax entries of its own channel (:189)
-    const int w = idx % W;
-    const int h = (idx / W) % H;
-    const int cc = (idx / (W * H)) % C;
-    const int nn = idx / (W * H * C);
-    if (nn != g.batch || cc != c) continue;
+    // decode the cell: the reference's thread for cell `idx` only looks at RoIs of its own image
+    // (:150) and at argmax entries of its own channel (:189) -- i.e. idx must lie in the plane of
+    // (this RoI's image, this channel); then one division gives the cell
+    const int rem = idx - (g.batch * C + c) * HW;
+    if (rem < 0 || rem >= HW) continue;
+    const int h = rem / W;
+    const int w = rem - h * W;
     if (!(w >= g.sw && w <= g.ew && h >= g.sh && h <= g.eh)) continue;  // :157-159
     int phs = (int)floorf(__fdiv_rn((float)(h - g.sh), g.bin_h));       // :178-186
     int phe = (int)ceilf(__fdiv_rn((float)(h - g.sh + 1), g.bin_h));
@@ -151,9 +157,9 @@ extern "C" int tlod_roi_pool_forward(const float* features, const float* rois, f
   dim3 grid = pool_grid(num_rois, channels, pooled_h * pooled_w, &cpb);
   {
     LaunchScope scope("roi_pool_fwd_kernel", (cudaStream_t)stream);
-    roi_pool_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(features, rois, output, argmax, batch,
-                                                                channels, height, width, pooled_h,
-                                                                pooled_w, spatial_scale, cpb);
+    auto kern = (pooled_h == 7 && pooled_w == 7) ? roi_pool_fwd_kernel<7, 7> : roi_pool_fwd_kernel<0, 0>;
+    kern<<<grid, 256, 0, (cudaStream_t)stream>>>(features, rois, output, argmax, batch, channels, height, width,
+                                                 pooled_h, pooled_w, spatial_scale, cpb);
   }
   return last_launch_status();
 }
@@ -175,8 +181,9 @@ extern "C" int tlod_roi_pool_backward(const float* top_grad, const int* argmax, 
   dim3 grid = pool_grid(num_rois, channels, pooled_h * pooled_w, &cpb);
   {
     LaunchScope scope("roi_pool_bwd_kernel", st);
-    roi_pool_bwd_kernel<<<grid, 256, 0, st>>>(top_grad, argmax, rois, bottom_grad, batch, channels,
-                                              height, width, pooled_h, pooled_w, spatial_scale, cpb);
+    auto kern = (pooled_h == 7 && pooled_w == 7) ? roi_pool_bwd_kernel<7, 7> : roi_pool_bwd_kernel<0, 0>;
+    kern<<<grid, 256, 0, st>>>(top_grad, argmax, rois, bottom_grad, batch, channels, height, width, pooled_h,
+                               pooled_w, spatial_scale, cpb);
   }
   return last_launch_status();
 }
