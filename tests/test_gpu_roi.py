@@ -246,3 +246,46 @@ def test_full_size_adjointness_cfg3():
     sub = rois[idx].cpu()
     ref = orc.roi_align_forward(x[:, :8].cpu().numpy(), sub.numpy(), 8, 8, 1 / 16)
     assert rel_err(y[idx][:, :8].cpu().numpy(), ref) <= 1e-5
+
+
+@pytest.mark.parametrize("tag", ["cfg1_vgg_conv5", "bwd_two_channels_per_lane", "bwd_wide_rows", "aligned_14x14"])
+def test_roi_align_writes_stay_inside_the_callers_buffers(tag):
+    """The C ABI works on caller-owned memory: plan, output and gradient are carved out of larger
+    sentinel-filled allocations and the bytes around them must come back untouched (the TMA-stored
+    forward tiles, the row-resident backward and the plan's row lists all compute their own
+    addresses)."""
+    from tlod_b200 import functional as F
+    from tlod_b200._lib import check, lib
+    B, C, H, W, R, AH, AW, scale = ALIGN_CASES[tag]
+    feat, rois, AH, AW, scale = _case(tag)
+    fd, rd = feat.to(DEV), rois.to(DEV)
+    PAD = 4096  # floats; keeps the 128-byte alignment of the carved buffers
+    SENT = 12345.0
+
+    def carve(numel):
+        big = torch.full((numel + 2 * PAD,), SENT, dtype=torch.float32, device=DEV)
+        return big, big[PAD:PAD + numel]
+
+    def untouched(big, numel):
+        return bool((big[:PAD] == SENT).all()) and bool((big[PAD + numel:] == SENT).all())
+
+    nplan = (lib.tlod_roi_align_plan_bytes(B, R) + 3) // 4
+    plan_big, plan = carve(nplan)
+    out_big, out = carve(R * C * AH * AW)
+    grad_big, grad = carve(B * C * H * W)
+    top = torch.randn(R, C, AH, AW, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    check(lib.tlod_roi_align_plan(rd.data_ptr(), B, H, W, R, AH, AW, scale, plan.data_ptr(), nplan * 4, st), "plan")
+    check(lib.tlod_roi_align_forward(fd.data_ptr(), rd.data_ptr(), out.data_ptr(), B, C, H, W, R, AH, AW, scale,
+                                     plan.data_ptr(), nplan * 4, st), "forward")
+    check(lib.tlod_roi_align_backward(top.data_ptr(), rd.data_ptr(), grad.data_ptr(), B, C, H, W, R, AH, AW, scale,
+                                      plan.data_ptr(), nplan * 4, st), "backward")
+    torch.cuda.synchronize()
+    assert untouched(plan_big, nplan) and untouched(out_big, out.numel()) and untouched(grad_big, grad.numel())
+    ref = F.roi_align_forward(fd, rd, AH, AW, scale)
+    assert torch.equal(out.view_as(ref), ref)
+    refg = F.roi_align_backward(top, rd, feat.shape, scale)
+    if AW == 8 and C % 32 == 0:  # row-resident backward: fixed summation order
+        assert torch.equal(grad.view_as(refg), refg)
+    else:                        # generic backward: fp32 atomics, order varies
+        assert rel_err(grad.view_as(refg).cpu().numpy(), refg.cpu().numpy()) <= 1e-5
