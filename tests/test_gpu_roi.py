@@ -289,3 +289,26 @@ def test_roi_align_writes_stay_inside_the_callers_buffers(tag):
         assert torch.equal(grad.view_as(refg), refg)
     else:                        # generic backward: fp32 atomics, order varies
         assert rel_err(grad.view_as(refg).cpu().numpy(), refg.cpu().numpy()) <= 1e-5
+
+
+@pytest.mark.parametrize("shape", [(8, 1024, 38, 75, 2048), (2, 512, 37, 75, 512), (1, 64, 37, 75, 128)])
+def test_roi_align_backward_is_bitwise_stable_over_repeated_launches(shape):
+    """The row-resident backward has a fixed summation order and recycles its TMA stages right
+    after reading them: thirty back-to-back launches must give bit-identical gradients (a stage
+    refilled too early, or any other race, would show here)."""
+    from tlod_b200 import functional as F
+    B, C, H, W, R = shape
+    rois = synth_rois(R, B, 41).to(DEV)
+    g = torch.Generator().manual_seed(17)
+    top = torch.randn(R, C, 8, 8, generator=g).to(DEV)
+    plan = F.roi_align_plan(rois, (B, C, H, W), 8, 8, 1 / 16)
+    first = F.roi_align_backward(top, rois, (B, C, H, W), 1 / 16, plan=plan)
+    for _ in range(30):
+        again = F.roi_align_backward(top, rois, (B, C, H, W), 1 / 16, plan=plan)
+        assert torch.equal(first, again)
+    fwd0 = None
+    feat = features(B, C, H, W, 3).to(DEV)
+    for _ in range(10):
+        out = F.roi_align_forward(feat, rois, 8, 8, 1 / 16, plan=plan)
+        fwd0 = out if fwd0 is None else fwd0
+        assert torch.equal(fwd0, out)
