@@ -60,9 +60,15 @@ __device__ __forceinline__ float4 load_box(const float* __restrict__ p, int stri
   return make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
 }
 
-// Words per mask row: the column blocks, padded to a multiple of 4 so that every row starts on
-// a 32-byte sector and the scan can fetch four words per load.
-__host__ __device__ inline int nms_row_words(int n) { return (((n + 63) >> 6) + 3) & ~3; }
+// Mask layout, per image: word-major, mask[word j][row r] with rows padded to whole chunks --
+// the 64 rows of a chunk at one word are 512 contiguous bytes, so the scan fetches them with
+// fully coalesced loads.  (A row-major mask made every scan load a gather of one 32-byte sector
+// per lane: 32 tag lookups per instruction on the single SM that scans an image, ~2000 cycles
+// per chunk.)
+__host__ __device__ inline int nms_rows_padded(int n) { return ((n + 63) >> 6) << 6; }
+__host__ __device__ inline size_t nms_mask_words(int n) {
+  return (size_t)((n + 63) >> 6) * (size_t)nms_rows_padded(n);
+}
 
 // Per-image scan state carried from one phase to the next.
 struct NmsState {
@@ -86,12 +92,12 @@ __host__ __device__ inline int nms_phase_end(int n, int max_keep, int phase /* 1
 // Persistent grid (gridDim.x CTAs per image, blockIdx.y = image); 256 threads: thread t owns
 // row t & 63 of a 64x64 tile and 16 of its 64 columns (quarter t >> 6).  The tiles of a phase are the pairs
 // (col block cb in [cb0, cb1), row block rb <= cb), numbered cb-major.
-// mask[(img * n + row) * rs + col_block]; in the diagonal tile the word holds every other box of
+// mask[img][col_block][row] (np = padded rows); in the diagonal tile the word holds every other box of
 // the chunk that overlaps the row's box (both directions).
 template <bool FILTER>
 __global__ void __launch_bounds__(256)
     nms_mask_kernel(const float* __restrict__ boxes, int n, int stride, float thresh,
-                    unsigned long long* __restrict__ mask, int rs, int cb0, int cb1, int first_phase,
+                    unsigned long long* __restrict__ mask, int np, int cb0, int cb1, int first_phase,
                     NmsState* __restrict__ state) {
   const int img = blockIdx.y;
   const int t = threadIdx.x;
@@ -145,7 +151,8 @@ __global__ void __launch_bounds__(256)
       // bit: commutative adds, min / max); the scan derives "earlier boxes that overlap me" from it
       if (row_blk == col_blk && (r >> 4) == q) bits &= ~(1u << (r & 15));
       // the row's 64-bit word is written as its four 16-bit quarters (little endian)
-      unsigned short* w16 = reinterpret_cast<unsigned short*>(mask + ((size_t)img * n + row) * rs + col_blk);
+      unsigned short* w16 = reinterpret_cast<unsigned short*>(
+          mask + (size_t)img * nms_mask_words(n) + (size_t)col_blk * np + row);
       w16[q] = (unsigned short)bits;
     }
   }
@@ -237,14 +244,14 @@ __global__ void __launch_bounds__(SCAN_THREADS)
     nms_scan_kernel(const unsigned long long* __restrict__ mask, int n, int max_keep,
                     int* __restrict__ keep_out, int keep_stride, int* __restrict__ num_out,
                     const float* __restrict__ boxes, int box_stride, float* __restrict__ rois_out,
-                    int post, int c0, int c1, int last_phase, NmsState* __restrict__ state, int rs) {
+                    int post, int c0, int c1, int last_phase, NmsState* __restrict__ state, int np) {
   extern __shared__ unsigned long long remv[];  // ncb words (only [c0, c1) are used)
   __shared__ unsigned long long kept_sh[2];
   __shared__ int done_sh[2];
   __shared__ int nkeep_sh;
   const int img = blockIdx.x;
   if (state[img].done) return;
-  const unsigned long long* m = mask + (size_t)img * n * rs;
+  const unsigned long long* m = mask + (size_t)img * nms_mask_words(n);  // m[word * np + row]
   int* keep = keep_out + (size_t)img * keep_stride;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int nkeep0 = state[img].nkeep;
@@ -255,7 +262,7 @@ __global__ void __launch_bounds__(SCAN_THREADS)
     for (int k = lane; k < nkeep0; k += 32 * 4) {
       unsigned long long v[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = (k + 32 * u < nkeep0) ? m[(size_t)keep[k + 32 * u] * rs + j] : 0ULL;
+      for (int u = 0; u < 4; ++u) v[u] = (k + 32 * u < nkeep0) ? m[(size_t)j * np + keep[k + 32 * u]] : 0ULL;
       acc |= v[0] | v[1] | v[2] | v[3];
     }
     acc = warp_or_u64(acc);
@@ -270,19 +277,21 @@ __global__ void __launch_bounds__(SCAN_THREADS)
   unsigned long long s2a = 0, s2b = 0;    // rows of chunk c-2 at word c
   unsigned long long kept1 = 0ULL, kept2 = 0ULL;  // survivors of chunks c-1, c-2 (this phase)
   if (wid == 0 && c0 < c1) {
-    if (64 * c0 + lane < n) d0 = m[(size_t)(64 * c0 + lane) * rs + c0];
-    if (64 * c0 + lane + 32 < n) d1 = m[(size_t)(64 * c0 + lane + 32) * rs + c0];
+    if (64 * c0 + lane < n) d0 = m[(size_t)c0 * np + 64 * c0 + lane];
+    if (64 * c0 + lane + 32 < n) d1 = m[(size_t)c0 * np + 64 * c0 + lane + 32];
   }
-  // ---- helper state: loads in flight (issued in iteration c, folded in iteration c + 1) ----
-  // Helper warp h (1..7) owns the groups of four consecutive words (one 32-byte sector per
-  // mask row) g = h - 1, h - 1 + 7, ...; lane l loads the sectors of rows l and l + 32 of the
-  // chunk if those boxes survived.
+  // ---- helper state ----
+  // Helper warp h (1..HW) owns the words c0 + (h-1) + u * HW, u < MAXW.  For every chunk it loads
+  // the chunk's 64 rows at its words (two coalesced 256-byte loads per word: lane l holds rows l
+  // and l + 32), ORs the survivors' rows into lane-private partial words one iteration later, and
+  // reduces a word across the lanes once, two barriers before warp 0 reads it (REDUX is scarce).
   constexpr int HW = SCAN_THREADS / 32 - 1;  // helper warps
-  constexpr int MAXG = 4;                    // word groups per helper warp kept in flight
-  ulonglong4 pend[MAXG][2];
-  ulonglong4 acc[MAXG];  // lane-private OR of the rows folded so far, per owned word group
+  constexpr int MAXW = 10;                   // words per helper warp: HW * MAXW = 70 words per phase
+  unsigned long long pend[MAXW][2];          // loads in flight (issued in iteration c, folded in c + 1)
+  unsigned long long acc[MAXW];              // lane-private OR of the survivors' rows so far
 #pragma unroll
-  for (int u = 0; u < MAXG; ++u) acc[u] = make_ulonglong4(0ULL, 0ULL, 0ULL, 0ULL);
+  for (int u = 0; u < MAXW; ++u) acc[u] = 0ULL;
+  unsigned long long pend_kept = 0ULL;       // survivors of the chunk the pending loads belong to
   int pend_c = -1;
   for (int c = c0; c < c1; ++c) {
     if (wid == 0) {
@@ -291,13 +300,13 @@ __global__ void __launch_bounds__(SCAN_THREADS)
       if (c + 1 < c1) {  // then chunks <= c are full: all their rows exist
         const int w1 = c + 1;
         const int r0 = 64 * w1 + lane, r1 = r0 + 32;
-        if (r0 < n) nd0 = m[(size_t)r0 * rs + w1];
-        if (r1 < n) nd1 = m[(size_t)r1 * rs + w1];
-        n1a = m[(size_t)(64 * c + lane) * rs + w1];
-        n1b = m[(size_t)(64 * c + 32 + lane) * rs + w1];
+        if (r0 < n) nd0 = m[(size_t)w1 * np + r0];
+        if (r1 < n) nd1 = m[(size_t)w1 * np + r1];
+        n1a = m[(size_t)w1 * np + 64 * c + lane];
+        n1b = m[(size_t)w1 * np + 64 * c + 32 + lane];
         if (c >= c0 + 1) {
-          n2a = m[(size_t)(64 * (c - 1) + lane) * rs + w1];
-          n2b = m[(size_t)(64 * (c - 1) + 32 + lane) * rs + w1];
+          n2a = m[(size_t)w1 * np + 64 * (c - 1) + lane];
+          n2b = m[(size_t)w1 * np + 64 * (c - 1) + 32 + lane];
         }
       }
       unsigned long long urgent = 0ULL;
@@ -333,70 +342,50 @@ __global__ void __launch_bounds__(SCAN_THREADS)
     if (done_sh[c & 1]) break;
     if (wid != 0) {
       const int h = wid - 1;
-      const int gbase = c0 >> 2;  // helper h owns the word groups gbase + h + u * HW, u < MAXG
-      // 1. the sectors loaded one iteration ago (rows of chunk c-1's survivors) join the lane's
-      //    private partial ORs: no cross-lane reduction here (REDUX is the scarce resource: the
-      //    per-chunk reduction of every word took 224 of them per iteration)
+      // 1. the rows loaded one iteration ago (chunk c-1), masked by that chunk's survivors
       if (pend_c >= 0) {
+        const bool s0 = (pend_kept >> lane) & 1ULL, s1 = (pend_kept >> (lane + 32)) & 1ULL;
 #pragma unroll
-        for (int u = 0; u < MAXG; ++u) {
-          acc[u].x |= pend[u][0].x | pend[u][1].x;
-          acc[u].y |= pend[u][0].y | pend[u][1].y;
-          acc[u].z |= pend[u][0].z | pend[u][1].z;
-          acc[u].w |= pend[u][0].w | pend[u][1].w;
-        }
+        for (int u = 0; u < MAXW; ++u) acc[u] |= (s0 ? pend[u][0] : 0ULL) | (s1 ? pend[u][1] : 0ULL);
         pend_c = -1;
       }
       // 2. word c + 2 now holds the survivors of every chunk <= c - 1 (those of chunks c, c + 1
-      //    reach it through warp 0's s1 / s2 path): reduce it across the lanes, once, two
-      //    barriers before warp 0 reads it
+      //    reach it through warp 0's s1 / s2 path): reduce it across the lanes, once
       {
-        const int j = c + 2;
-        const int gj = (j >> 2) - gbase;
-        if (j < c1 && gj % HW == h && gj / HW < MAXG) {
-          const int uo = gj / HW, qo = j & 3;
+        const int j = c + 2, rel = j - c0;
+        if (j < c1 && rel % HW == h && rel / HW < MAXW) {
+          const int uo = rel / HW;
           unsigned long long v = 0ULL;
 #pragma unroll
-          for (int u = 0; u < MAXG; ++u)
-            if (u == uo) v = qo == 0 ? acc[u].x : qo == 1 ? acc[u].y : qo == 2 ? acc[u].z : acc[u].w;
+          for (int u = 0; u < MAXW; ++u)
+            if (u == uo) v = acc[u];
           v = warp_or_u64(v);
           if (lane == 0) remv[j] |= v;
         }
       }
-      // 3. rows of chunk c's survivors -> words [c+3, c1)
+      // 3. rows of chunk c at this warp's words >= c + 3 (the rows exist: c + 3 < c1)
       const unsigned long long k = kept_sh[c & 1];
       if (k && c + 3 < c1) {
-        const bool s0 = (k >> lane) & 1ULL, s1 = (k >> (lane + 32)) & 1ULL;
-        const ulonglong4 zero = make_ulonglong4(0ULL, 0ULL, 0ULL, 0ULL);
-        const unsigned long long* r0 = m + (size_t)(64 * c + lane) * rs;
-        const unsigned long long* r1 = m + (size_t)(64 * c + lane + 32) * rs;
+        const unsigned long long* rows = m + 64 * c + lane;
 #pragma unroll
-        for (int u = 0; u < MAXG; ++u) {
-          const int g = gbase + h + u * HW;
-          pend[u][0] = zero;
-          pend[u][1] = zero;
-          if (4 * g < c1 && 4 * g + 3 >= c + 3) {
-            if (s0) pend[u][0] = *reinterpret_cast<const ulonglong4*>(r0 + 4 * g);
-            if (s1) pend[u][1] = *reinterpret_cast<const ulonglong4*>(r1 + 4 * g);
+        for (int u = 0; u < MAXW; ++u) {
+          const int j = c0 + h + u * HW;
+          pend[u][0] = 0ULL;
+          pend[u][1] = 0ULL;
+          if (j >= c + 3 && j < c1) {
+            pend[u][0] = rows[(size_t)j * np];
+            pend[u][1] = rows[(size_t)j * np + 32];
           }
         }
         pend_c = c;
-        // phases wider than MAXG * HW * 4 = 112 words: the rest, reduced per chunk
-        for (int g = gbase + h + MAXG * HW; 4 * g < c1; g += HW) {
-          if (4 * g + 3 < c + 3) continue;
-          unsigned long long w[4] = {0ULL, 0ULL, 0ULL, 0ULL};
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (4 * g + q < c1) {
-              if (s0) w[q] |= r0[4 * g + q];
-              if (s1) w[q] |= r1[4 * g + q];
-            }
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const unsigned long long v = warp_or_u64(w[q]);
-            if (lane == 0 && 4 * g + q >= c + 3 && 4 * g + q < c1) remv[4 * g + q] |= v;
-          }
+        pend_kept = k;
+        // phases wider than HW * MAXW = 70 words: the rest, reduced per chunk
+        const bool s0 = (k >> lane) & 1ULL, s1 = (k >> (lane + 32)) & 1ULL;
+        for (int j = c0 + h + MAXW * HW; j < c1; j += HW) {
+          if (j < c + 3) continue;
+          const unsigned long long w = (s0 ? rows[(size_t)j * np] : 0ULL) | (s1 ? rows[(size_t)j * np + 32] : 0ULL);
+          const unsigned long long v = warp_or_u64(w);
+          if (lane == 0) remv[j] |= v;
         }
       }
     }
@@ -717,7 +706,7 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 static int launch_mask_scan(const float* boxes, int batch, int n, int stride, float thresh,
                             int max_keep, unsigned long long* mask, int* keep, int keep_stride,
                             int* num, float* rois_out, int post, NmsState* state, cudaStream_t st) {
-  const int ncb = (n + 63) / 64, rs = nms_row_words(n);
+  const int ncb = (n + 63) / 64, np = nms_rows_padded(n);
   if (batch > 65535) return TLOD_ERR_UNSUPPORTED;
   const bool filter = thresh >= 1e-6f && thresh <= 1e6f;
   int prev = 0;
@@ -732,10 +721,10 @@ static int launch_mask_scan(const float* boxes, int batch, int n, int stride, fl
     {
       LaunchScope scope("nms_mask_kernel", st);
       if (filter)
-        nms_mask_kernel<true><<<grid, 256, 0, st>>>(boxes, n, stride, thresh, mask, rs, c0, c1, phase == 1,
+        nms_mask_kernel<true><<<grid, 256, 0, st>>>(boxes, n, stride, thresh, mask, np, c0, c1, phase == 1,
                                                     state);
       else
-        nms_mask_kernel<false><<<grid, 256, 0, st>>>(boxes, n, stride, thresh, mask, rs, c0, c1, phase == 1,
+        nms_mask_kernel<false><<<grid, 256, 0, st>>>(boxes, n, stride, thresh, mask, np, c0, c1, phase == 1,
                                                      state);
     }
     int rc = last_launch_status();
@@ -744,7 +733,7 @@ static int launch_mask_scan(const float* boxes, int batch, int n, int stride, fl
       LaunchScope scope("nms_scan_kernel", st);
       nms_scan_kernel<<<batch, SCAN_THREADS, (size_t)ncb * 8, st>>>(mask, n, max_keep, keep, keep_stride, num,
                                                                   boxes, stride, rois_out, post, c0, c1,
-                                                                  end >= n, state, rs);
+                                                                  end >= n, state, np);
     }
     rc = last_launch_status();
     if (rc) return rc;
@@ -759,7 +748,7 @@ using namespace tlod;
 
 extern "C" size_t tlod_nms_workspace_bytes(int n) {
   if (n <= 0) return 16;
-  return align_up((size_t)n * nms_row_words(n) * 8, 256) + 256;  // mask + NmsState
+  return align_up(nms_mask_words(n) * 8, 256) + 256;  // mask + NmsState
 }
 
 extern "C" int tlod_nms(const float* boxes, int n, int box_stride, float thresh, int max_keep,
@@ -777,7 +766,7 @@ extern "C" int tlod_nms(const float* boxes, int n, int box_stride, float thresh,
   if (n > (1 << 20)) return TLOD_ERR_UNSUPPORTED;
   if (max_keep <= 0 || max_keep > n) max_keep = n;
   if ((uintptr_t)workspace & 31) return TLOD_ERR_WORKSPACE;
-  NmsState* state = (NmsState*)((unsigned char*)workspace + align_up((size_t)n * nms_row_words(n) * 8, 256));
+  NmsState* state = (NmsState*)((unsigned char*)workspace + align_up(nms_mask_words(n) * 8, 256));
   return launch_mask_scan(boxes, 1, n, box_stride, thresh, max_keep,
                           (unsigned long long*)workspace, keep_out, n, num_out, nullptr, 0, state, st);
 }
@@ -796,10 +785,9 @@ struct ProposalWs {
 };
 static ProposalWs proposal_ws(int batch, int n_sorted, int post, int nruns) {
   ProposalWs w;
-  const size_t ncb = (size_t)nms_row_words(n_sorted);
   size_t off = 0;
   w.boxes = off; off = align_up(off + (size_t)batch * n_sorted * 16, 256);
-  w.mask = off;  off = align_up(off + (size_t)batch * n_sorted * ncb * 8, 256);
+  w.mask = off;  off = align_up(off + (size_t)batch * nms_mask_words(n_sorted) * 8, 256);
   w.keep = off;  off = align_up(off + (size_t)batch * (post > 0 ? post : n_sorted) * 4, 256);
   w.num = off;   off = align_up(off + (size_t)batch * 4, 256);
   w.state = off; off = align_up(off + (size_t)batch * sizeof(NmsState), 256);
@@ -870,7 +858,7 @@ extern "C" int tlod_class_nms_padded_rows(int num_rois) { return num_rois > 0 ? 
 extern "C" size_t tlod_class_nms_workspace_bytes(int num_rois, int num_classes) {
   if (num_rois <= 0 || num_classes <= 0) return 256;
   const int Rp = cn_pow2(num_rois);
-  return align_up((size_t)num_classes * Rp * nms_row_words(Rp) * 8, 256) +
+  return align_up((size_t)num_classes * nms_mask_words(Rp) * 8, 256) +
          align_up((size_t)num_classes * sizeof(NmsState), 256) + 256;
 }
 
@@ -891,7 +879,7 @@ extern "C" int tlod_class_nms(const float* scores, const float* boxes, int num_r
   const int Rp = cn_pow2(num_rois), nc = num_classes - first_class;
   unsigned char* base = (unsigned char*)workspace;
   unsigned long long* mask = (unsigned long long*)base;
-  NmsState* state = (NmsState*)(base + align_up((size_t)num_classes * Rp * nms_row_words(Rp) * 8, 256));
+  NmsState* state = (NmsState*)(base + align_up((size_t)num_classes * nms_mask_words(Rp) * 8, 256));
   {
     LaunchScope scope("class_sort_kernel", st);
     class_sort_kernel<<<nc, CN_THREADS, 0, st>>>(scores, boxes, num_rois, num_classes, first_class, box_cols,
