@@ -3,7 +3,7 @@
 // Reference semantics: lib/model/roi_align/src/roi_align_kernel.cu:15-70 (fwd),
 // :94-143 (bwd); glue lib/model/roi_align/src/roi_align_cuda.c.
 //
-// Three pieces:
+// The pieces:
 //
 //  * the *plan* (tlod_roi_align_plan): everything that depends only on the RoIs and the
 //    map geometry, computed once per `rois` tensor and shared by the forward and the
@@ -21,12 +21,8 @@
 //    and the two slots always read cells of opposite column parity, so every shared-memory
 //    gather is bank-conflict free for any RoI geometry.
 //
-//  * band-resident backward (no global atomics, no memset): a CTA owns the gradient planes
-//    of (image, 128-channel group, row band) in shared memory.  Lane = channel: a plane is
-//    only ever touched by one thread, so the scatter is plain load-add-store on shared
-//    memory, with a fixed summation order (bitwise reproducible); the band is written to
-//    HBM once with coalesced stores.  The reference issues 4*R*C*AH*AW global fp32 REDs
-//    (roi_align_kernel.cu:131-134).
+//  * row-resident backward (no global atomics, no memset): roi_align_bwd.cu.  The plan holds
+//    its per-(image, plane row) lists of gradient rows.
 //
 //  * generic kernels for shapes the resident layouts cannot hold (channels % 16 != 0,
 //    planes too large for shared memory, aligned size > 16, no plan): one CTA per

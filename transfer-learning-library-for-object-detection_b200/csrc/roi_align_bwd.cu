@@ -3,25 +3,26 @@
 // Reference semantics: lib/model/roi_align/src/roi_align_kernel.cu:94-143 (4 fp32 atomicAdd
 // per output element, 537 M at BASELINE cfg3); glue roi_align_cuda.c:42-76.
 //
-// One warp (= one CTA) owns one row of the gradient map for 32 channels:
-// (image b, plane row y, channels 32g .. 32g+31).  Lane = channel, so a cell is only ever
+// One warp owns one row of the gradient map for 32 (or 64) channels: (image b, plane row y,
+// channel group g).  Lane = channel (or the channel pair c, c + 32), so a cell is only ever
 // touched by one thread: the scatter is plain load-add-store on shared memory in a fixed order
 // (bitwise reproducible), and the finished row is written to HBM once, coalesced.
 //
 // The plan (roi_align.cu) holds, per (image, plane row), the list of gradient rows (RoI n,
 // output row ph, row weight) that feed it.  The warp walks its list:
-//   * lane 0 fetches the 32-byte gradient rows of the warp's 32 channels (256 B apart in HBM)
-//     with one TMA tile copy (tensor map over (R, C, AH, 8), box 8 x 1 x 32 x 1, 32-byte
-//     swizzle) into a private ring of stages, and the RoI's column chain (BwdCols, 208 B) with
-//     a bulk copy on the same mbarrier when the RoI changes;
+//   * one elected lane fetches the 32-byte gradient rows of the warp's channels (256 B apart in
+//     HBM) with one TMA tile copy (tensor map over (R, C, AH, 8), box 8 x 1 x 32|64 x 1, 32-byte
+//     swizzle) into a private ring of stages, and the RoI's column chain (BwdCols, 96 or 224 B)
+//     with a bulk copy on the same mbarrier when the RoI changes;
 //   * every lane reads its channel's row with two conflict-free LDS.128 and adds weight * row
 //     into 8 registers -- all output rows of a RoI have the same column structure, so the rows
 //     that feed this plane row are summed first;
 //   * when the RoI changes, the column chain turns the 8 sums into <= 16 distinct cells, which
 //     are added to the row: 16 loads, 16 adds, 16 stores, no predicates (sites that are not
 //     emitted point at a dump cell behind the row).
-// Warps are independent: no block-wide synchronisation anywhere, and the grid (B * H * C/32
-// one-warp CTAs) is balanced by the hardware scheduler.
+// Warps are independent: no synchronisation between rows, and the grid (B * H * C/32 or C/64
+// CTAs) is balanced by the hardware scheduler.  On small grids a CTA has K warps that split the
+// row's list and sum their copies of the row at the end.
 #include "async_copy.cuh"
 #include "roi_align_plan.cuh"
 
@@ -32,7 +33,7 @@ constexpr int RW_META_BYTES = 256;  // BwdCols (224), padded: keeps the tiles' s
 // CPL = channels per lane (1 or 2): a warp owns 32 * CPL channels of its row.  With CPL = 2 a
 // cell holds the pair (channel lane, channel lane + 32) as a float2: one 64-bit shared-memory
 // access updates both, and the per-item bookkeeping and the column state are paid once per 64
-// channels -- but a warp needs twice the shared memory, so it is used on large grids only.
+// channels -- but a warp needs twice the shared memory.  Used whenever channels % 64 == 0.
 __host__ __device__ constexpr int rw_tile_bytes(int cpl) { return 32 * 32 * cpl; }  // 32-byte rows
 __host__ __device__ constexpr int rw_stage_bytes(int cpl) { return rw_tile_bytes(cpl) + RW_META_BYTES; }
 // bytes of shared memory one warp owns: [stages][row: 32 lanes x Ws cells x CPL floats][full barriers]
