@@ -16,10 +16,11 @@
 //    slab) in shared memory (16 x H*W fp32 = 178-182 KB for the 37x75 / 38x75 maps) and
 //    streams the image's RoIs through them.  HBM traffic is the algorithmic minimum: each
 //    plane is read once, the (R, C, AH, AW) tensor is written once with full 32-byte
-//    sectors.  Lane = 2*channel + slot; slot = half of an output row (4 samples).  The
-//    plane stride is 2 (mod 4) floats so the 16 channels land on 16 banks of one parity,
-//    and the two slots always read cells of opposite column parity, so every shared-memory
-//    gather is bank-conflict free for any RoI geometry.
+//    sectors (8x8 outputs: through per-warp staging tiles and TMA tensor stores).  Lane =
+//    (channel, slot); slot = parity of the output row.  The plane stride is 2 (mod 4) floats
+//    so the 16 channels land on 16 banks of one parity, and the two slots always read cells
+//    of opposite column parity, so every shared-memory gather is bank-conflict free for any
+//    RoI geometry.
 //
 //  * row-resident backward (no global atomics, no memset): roi_align_bwd.cu.  The plan holds
 //    its per-(image, plane row) lists of gradient rows.
