@@ -114,6 +114,26 @@ int tlod_avgpool2x2_forward(const float* in, float* out, long long tiles, int he
 int tlod_avgpool2x2_backward(const float* grad_out, float* grad_in, long long tiles, int height,
                              int width, void* stream);
 
+/* RoIAlignAvg in one call (lib/model/roi_align/modules/roi_align.py:20-29): RoIAlign at
+ * (pooled_h + 1, pooled_w + 1) samples followed by avg_pool2d(kernel_size=2, stride=1).
+ * output / top_grad are (num_rois, channels, pooled_h, pooled_w); `plan` is the plan built for
+ * aligned size (pooled_h + 1, pooled_w + 1).
+ * Forward: for pooled 7 x 7 (the only size the reference uses), channels % 16 == 0 and a plan,
+ * ONE kernel produces the pooled tensor; the (R, C, 8, 8) sample tensor is never written and
+ * `scratch` may be NULL.  Other shapes run RoIAlign into `scratch` and then the 2x2 average
+ * (TLOD_ERR_WORKSPACE if scratch is missing or smaller than tlod_roi_align_avg_scratch_bytes).
+ * Backward: the adjoint of the average is written into `scratch` (always required), then
+ * tlod_roi_align_backward runs on it; bottom_grad is fully overwritten. */
+size_t tlod_roi_align_avg_scratch_bytes(int channels, int num_rois, int pooled_h, int pooled_w);
+int tlod_roi_align_avg_forward(const float* features, const float* rois, float* output, int batch,
+                               int channels, int height, int width, int num_rois, int pooled_h,
+                               int pooled_w, float spatial_scale, const void* plan, size_t plan_bytes,
+                               void* scratch, size_t scratch_bytes, void* stream);
+int tlod_roi_align_avg_backward(const float* top_grad, const float* rois, float* bottom_grad,
+                                int batch, int channels, int height, int width, int num_rois,
+                                int pooled_h, int pooled_w, float spatial_scale, const void* plan,
+                                size_t plan_bytes, void* scratch, size_t scratch_bytes, void* stream);
+
 /* ------------------------------------------------------------------------ */
 /* RoIPool                                                                    */
 /* replaces roi_pooling_forward_cuda / roi_pooling_backward_cuda              */

@@ -132,6 +132,78 @@ def test_avgpool2x2_matches_torch(shape):
     assert rel_err(gx.cpu().numpy(), xr.grad.numpy()) <= 1e-6
 
 
+AVG_CASES = ["cfg1_vgg_conv5", "multi_image_res_conv4", "channels_not_x16", "plane_too_big_for_smem",
+             "many_rois_one_image", "full_planes_no_bands", "bwd_one_warp_per_row", "raw_7x7", "odd_grid_3x5"]
+
+
+@pytest.mark.parametrize("tag", AVG_CASES)
+def test_roi_align_avg_forward_backward(tag):
+    """RoIAlignAvg in one call (fused 8x8 -> 7x7 kernel: bulk-staged and register-staged planes,
+    run-time and compile-time width; composed path for every other shape) against
+    avg_pool2d(oracle RoIAlign, 2, 1) and the adjoint chain."""
+    from tlod_b200 import functional as F
+    feat, rois, AH, AW, scale = _case(tag)
+    fd, rd = feat.to(DEV), rois.to(DEV)
+    plan = F.roi_align_plan(rd, feat.shape, AH, AW, scale)
+    out = F.roi_align_avg_forward(fd, rd, AH - 1, AW - 1, scale, plan=plan)
+    ref_s = torch.from_numpy(orc.roi_align_forward(feat.numpy(), rois.numpy(), AH, AW, scale))
+    ref = torch.nn.functional.avg_pool2d(ref_s, 2, 1)
+    assert out.shape == ref.shape
+    assert rel_err(out.cpu().numpy(), ref.numpy()) <= 1e-5
+    assert np.allclose(out.cpu().numpy(), ref.numpy(), rtol=1e-5, atol=1e-5)
+    top = torch.randn(ref.shape, generator=torch.Generator().manual_seed(6))
+    grad = F.roi_align_avg_backward(top.to(DEV), rd, feat.shape, scale, plan=plan).cpu().numpy()
+    r = ref_s.clone().requires_grad_(True)
+    torch.nn.functional.avg_pool2d(r, 2, 1).backward(top)
+    refg = orc.roi_align_backward(r.grad.numpy(), rois.numpy(), feat.shape, scale, accumulate_double=True)
+    assert rel_err(grad, refg) <= 1e-4
+    # without a plan the same entry point composes the generic kernels
+    out2 = F.roi_align_avg_forward(fd, rd, AH - 1, AW - 1, scale, plan=None)
+    assert rel_err(out2.cpu().numpy(), ref.numpy()) <= 1e-5
+
+
+def test_roi_align_avg_fused_edge_geometry_and_guard_band():
+    """Fused RoIAlignAvg on sub-cell to whole-map RoIs (every row-reuse code: same pair, shifted by
+    one, jump; clamped last rows; samples outside the map), an invalid image index, and the bytes
+    around the caller's output untouched by the bulk stores."""
+    from tlod_b200 import functional as F
+    from tlod_b200._lib import check, lib
+    B, C, H, W, scale = 3, 48, 38, 75, 1 / 16
+    g = torch.Generator().manual_seed(77)
+    R = 700
+    wpx = torch.cat([torch.rand(250, generator=g) * 40, torch.rand(250, generator=g) * 250,
+                     torch.rand(200, generator=g) * 1400])
+    hpx = torch.cat([torch.rand(250, generator=g) * 30, torch.rand(250, generator=g) * 160,
+                     torch.rand(200, generator=g) * 800])[torch.randperm(R, generator=g)]
+    x1 = torch.rand(R, generator=g) * 1250 - 40
+    y1 = torch.rand(R, generator=g) * 650 - 30
+    rois = torch.stack([torch.randint(0, B, (R,), generator=g).float(), x1, y1, x1 + wpx, y1 + hpx], 1)
+    rois[5, 0] = 7.0    # invalid image index -> zeros
+    rois[6, 0] = -2.0
+    feat = features(B, C, H, W, 78)
+    fd, rd = feat.to(DEV), rois.to(DEV)
+    PAD, SENT = 4096, 4321.0
+    n_out = R * C * 49
+    big = torch.full((n_out + 2 * PAD,), SENT, dtype=torch.float32, device=DEV)
+    out = big[PAD:PAD + n_out]
+    plan = F.roi_align_plan(rd, feat.shape, 8, 8, scale)
+    st = torch.cuda.current_stream().cuda_stream
+    check(lib.tlod_roi_align_avg_forward(fd.data_ptr(), rd.data_ptr(), out.data_ptr(), B, C, H, W, R, 7, 7, scale,
+                                         plan.data_ptr(), plan.numel(), None, 0, st), "avg forward (fused, no scratch)")
+    torch.cuda.synchronize()
+    assert bool((big[:PAD] == SENT).all()) and bool((big[PAD + n_out:] == SENT).all())
+    out = out.view(R, C, 7, 7).cpu().numpy()
+    assert np.all(out[5] == 0) and np.all(out[6] == 0)
+    keep = [i for i in range(R) if i not in (5, 6)]
+    ref_s = torch.from_numpy(orc.roi_align_forward(feat.numpy(), rois.numpy()[keep], 8, 8, scale))
+    ref = torch.nn.functional.avg_pool2d(ref_s, 2, 1).numpy()
+    assert rel_err(out[keep], ref) <= 1e-5
+    # 30 back-to-back launches: bit-identical (tile reuse / bulk-store ordering races would show)
+    first = F.roi_align_avg_forward(fd, rd, 7, 7, scale, plan=plan)
+    for _ in range(30):
+        assert torch.equal(first, F.roi_align_avg_forward(fd, rd, 7, 7, scale, plan=plan))
+
+
 def test_roi_align_invalid_batch_index_gives_zeros():
     from tlod_b200 import functional as F
     feat, rois, AH, AW, scale = _case("multi_image_res_conv4")

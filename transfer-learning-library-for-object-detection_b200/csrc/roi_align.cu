@@ -715,6 +715,10 @@ extern "C" int tlod_roi_align_forward(const float* features, const float* rois, 
   const bool planned = plan != nullptr && plan_supported(batch, height, width, aligned_h, aligned_w);
   if (plan && (plan_bytes < tlod_roi_align_plan_bytes(batch, num_rois) || ((uintptr_t)plan & 255)))
     return TLOD_ERR_WORKSPACE;
+  if (planned && aligned_h == 8 && aligned_w == 8) {
+    rc = roi_align_fwd8_launch(false, features, output, batch, channels, height, width, num_rois, plan, st);
+    if (rc != TLOD_ERR_UNSUPPORTED) return rc;
+  }
   if (planned && channels % PR_CH == 0 &&
       pr_smem_bytes(height, width, false) <= (size_t)device_info().max_smem_optin) {
     const int Pp = pr_plane_stride(height, width);

@@ -97,4 +97,9 @@ int roi_align_generic_launch(bool backward, const float* src, const float* rois,
                              int channels, int height, int width, int num_rois, int ah, int aw, float scale,
                              cudaStream_t st);
 
+// roi_align_fwd8.cu: the 8 x 8-sample forward (fused: RoIAlignAvg(7, 7) output).  Returns
+// TLOD_ERR_UNSUPPORTED, with nothing launched, for shapes it does not serve.
+int roi_align_fwd8_launch(bool fused, const float* features, float* output, int batch, int channels, int height,
+                          int width, int num_rois, const void* plan, cudaStream_t st);
+
 }  // namespace tlod

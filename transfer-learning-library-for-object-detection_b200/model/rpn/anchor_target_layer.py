@@ -9,6 +9,7 @@ random subsampling stays on the host with numpy's global RNG, consumed in exactl
 reference's order (:123-145), because the RNG stream position is data dependent: the (B, n)
 label array makes one pinned round trip (the reference synchronises 2 + 2B times)."""
 import ctypes
+import threading
 
 import numpy as np
 import torch
@@ -114,8 +115,9 @@ class _AnchorTargetLayer(nn.Module):
         self._num_anchors = self._anchors.size(0)
         self._allowed_border = 0
         self._cache = {}
-        self._stream = None
-        self._labels_host = None
+        self._streams = {}      # device index -> side stream of this layer
+        self._pinned_pool = {}  # (device index, shape, dtype) -> free pinned staging buffers
+        self._pool_lock = threading.Lock()
 
     def _inside(self, feat_h, feat_w, lim_w, lim_h, device):
         """Inside-image anchors for this map size (:66-91): (anchors (n,4), inds (n,), inverse (total,))."""
@@ -151,31 +153,47 @@ class _AnchorTargetLayer(nn.Module):
         rpn_cls_score, gt_boxes, im_info, num_boxes = input[0], input[1], input[2], input[3]
         height, width = rpn_cls_score.size(2), rpn_cls_score.size(3)
         dev = gt_boxes.device
-        if self._stream is None or self._stream.device != dev:
-            self._stream = torch.cuda.Stream(dev)
+        with self._pool_lock:
+            stream = self._streams.get(dev.index)
+            if stream is None:
+                stream = self._streams[dev.index] = torch.cuda.Stream(dev)
         cur = torch.cuda.current_stream(dev)
-        self._stream.wait_stream(cur)  # inputs produced on the caller's stream
-        with torch.cuda.stream(self._stream):
+        stream.wait_stream(cur)  # inputs produced on the caller's stream
+        with torch.cuda.stream(stream):
             # :86-87 -- the FIRST image's size, truncated to int, is used for the whole batch
             info0 = im_info[0].tolist()
             anchors, inds_inside, inv_index = self._inside(height, width, int(info0[1]), int(info0[0]), dev)
             labels, argmax = F.anchor_labels(anchors, gt_boxes, cfg.TRAIN.RPN_NEGATIVE_OVERLAP,
                                              cfg.TRAIN.RPN_POSITIVE_OVERLAP, cfg.TRAIN.RPN_CLOBBER_POSITIVES)
-            if self._labels_host is None or self._labels_host.shape != labels.shape:
-                self._labels_host = torch.empty(labels.shape, dtype=labels.dtype).pin_memory()
-            self._labels_host.copy_(labels, non_blocking=True)
+            # the pinned staging buffer travels with the returned state (begin() may be called again
+            # before finish(), e.g. by DataParallel replicas sharing this module's attributes)
+            labels_host = self._take_pinned(dev.index, tuple(labels.shape), labels.dtype)
+            labels_host.copy_(labels, non_blocking=True)
             copied = torch.cuda.Event()
-            copied.record(self._stream)
+            copied.record(stream)
         for t in (gt_boxes, im_info):
-            t.record_stream(self._stream)
-        return (labels, argmax, anchors, inv_index, gt_boxes, height, width, copied, cur)
+            t.record_stream(stream)
+        return (labels, argmax, anchors, inv_index, gt_boxes, height, width, copied, stream, labels_host)
+
+    def _take_pinned(self, dev_index, shape, dtype):
+        with self._pool_lock:
+            free = self._pinned_pool.setdefault((dev_index, shape, dtype), [])
+            if free:
+                return free.pop()
+        return torch.empty(shape, dtype=dtype).pin_memory()
+
+    def _give_pinned(self, dev_index, buf):
+        with self._pool_lock:
+            free = self._pinned_pool.setdefault((dev_index, tuple(buf.shape), buf.dtype), [])
+            if len(free) < 8:
+                free.append(buf)
 
     def finish(self, state):
-        labels, argmax, anchors, inv_index, gt_boxes, height, width, copied, cur = state
+        labels, argmax, anchors, inv_index, gt_boxes, height, width, copied, stream, labels_host = state
         batch_size = gt_boxes.size(0)
         A = self._num_anchors
         copied.synchronize()
-        lab = self._labels_host.numpy()  # (B, n) fp32 in {-1, 0, 1}: edited in place on the host
+        lab = labels_host.numpy()  # (B, n) fp32 in {-1, 0, 1}: edited in place on the host
 
         # ---- host-side subsampling, :118-145: same index order, same RNG draws ----
         num_fg = int(cfg.TRAIN.RPN_FG_FRACTION * cfg.TRAIN.RPN_BATCHSIZE)
@@ -191,11 +209,14 @@ class _AnchorTargetLayer(nn.Module):
             raise NotImplementedError("RPN_POSITIVE_WEIGHT >= 0 leaves the weights undefined in the "
                                       "reference as well (anchor_target_layer.py:159-164)")
 
-        with torch.cuda.stream(self._stream):
-            labels.copy_(self._labels_host, non_blocking=True)
+        with torch.cuda.stream(stream):
+            labels.copy_(labels_host, non_blocking=True)
             out = F.anchor_targets_finalize(labels, argmax, anchors, gt_boxes, inv_index, A, height, width,
                                             inside_w, positive_weights, negative_weights)
-        torch.cuda.current_stream(gt_boxes.device).wait_stream(self._stream)
+        torch.cuda.current_stream(gt_boxes.device).wait_stream(stream)
+        # the upload reads the pinned buffer asynchronously: it returns to the pool only for work
+        # queued on this device's side stream (begin() fills it there), which is ordered behind the upload
+        self._give_pinned(gt_boxes.device.index, labels_host)
         for t in out:
             t.record_stream(torch.cuda.current_stream(gt_boxes.device))
         return list(out)

@@ -32,6 +32,11 @@ SIGNATURES = {
                                         c_size_t, P]),
     "tlod_avgpool2x2_forward": (c_int, [P, P, c_longlong, c_int, c_int, P]),
     "tlod_avgpool2x2_backward": (c_int, [P, P, c_longlong, c_int, c_int, P]),
+    "tlod_roi_align_avg_scratch_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "tlod_roi_align_avg_forward": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P,
+                                           c_size_t, P, c_size_t, P]),
+    "tlod_roi_align_avg_backward": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P,
+                                            c_size_t, P, c_size_t, P]),
     "tlod_roi_pool_forward": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P]),
     "tlod_roi_pool_backward": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P]),
     "tlod_roi_crop_forward": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
@@ -75,6 +80,10 @@ SIGNATURES = {
     "tlod_da_loss_backward": (c_int, [P, P, P, c_int, P, P, c_float, c_float, c_float, P, P, c_int, c_int,
                                       c_int, c_int, P]),
 }
+
+
+ERR_UNSUPPORTED = -3  # TLOD_ERR_UNSUPPORTED
+ERR_WORKSPACE = -4    # TLOD_ERR_WORKSPACE
 
 
 class TlodError(RuntimeError):

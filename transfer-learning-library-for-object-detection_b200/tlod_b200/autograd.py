@@ -35,27 +35,26 @@ class RoIAlignFunction(Function):
 
 class RoIAlignAvgFunction(Function):
     """RoIAlign at (h+1, w+1) followed by the 2x2 stride-1 average (modules/roi_align.py:26-29) as
-    one autograd node: the (R, C, h+1, w+1) intermediate is not kept for backward (the average is
-    linear), and both halves run this library's kernels."""
+    one autograd node.  Forward: one kernel for 7 x 7 (the samples are averaged in registers, the
+    (R, C, 8, 8) tensor is never written).  Backward: the average's adjoint, then the row-resident
+    RoIAlign backward."""
 
     @staticmethod
     def forward(ctx, features, rois, aligned_height, aligned_width, spatial_scale):
         ctx.feature_size = tuple(features.shape)
         ctx.scale = float(spatial_scale)
-        ah, aw = int(aligned_height) + 1, int(aligned_width) + 1
-        plan = F.roi_align_plan(rois, ctx.feature_size, ah, aw, ctx.scale)
+        ph, pw = int(aligned_height), int(aligned_width)
+        plan = F.roi_align_plan(rois, ctx.feature_size, ph + 1, pw + 1, ctx.scale)
         ctx.has_plan = plan is not None
         ctx.save_for_backward(rois, *([plan] if ctx.has_plan else []))
-        x = F.roi_align_forward(features, rois, ah, aw, ctx.scale, plan=plan, use_plan=ctx.has_plan)
-        return F.avgpool2x2_forward(x)
+        return F.roi_align_avg_forward(features, rois, ph, pw, ctx.scale, plan=plan)
 
     @staticmethod
     def backward(ctx, grad_output):
         rois = ctx.saved_tensors[0]
         plan = ctx.saved_tensors[1] if ctx.has_plan else None
         assert grad_output.is_cuda
-        g = F.avgpool2x2_backward(grad_output)
-        grad_input = F.roi_align_backward(g, rois, ctx.feature_size, ctx.scale, plan=plan, use_plan=ctx.has_plan)
+        grad_input = F.roi_align_avg_backward(grad_output, rois, ctx.feature_size, ctx.scale, plan=plan)
         return grad_input, None, None, None, None
 
 

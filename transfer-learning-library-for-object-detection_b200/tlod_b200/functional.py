@@ -14,8 +14,6 @@ import torch
 from . import _lib
 from ._lib import check, lib
 
-_workspaces = {}
-
 
 def _require_cuda(*tensors):
     for t in tensors:
@@ -40,13 +38,14 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 def _workspace(device, nbytes: int, tag: str) -> torch.Tensor:
-    """Grow-only scratch buffer per (device, stream, tag)."""
-    key = (device.index, _stream(device), tag)
-    ws = _workspaces.get(key)
-    if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
-        _workspaces[key] = ws
-    return ws
+    """Scratch buffer for one call, from torch's caching allocator on the current stream.
+
+    Never shared between calls: a cached buffer per (device, stream) would be baked into every
+    CUDA graph captured on that stream, and graphs replayed concurrently (bench.py runs the source
+    and the target domain on two streams) would then race on it.  A per-call allocation is
+    stream-ordered when eager, and owned by the graph's private pool when captured."""
+    del tag
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
 # ---------------------------------------------------------------------------
@@ -65,9 +64,11 @@ def roi_align_plan(rois, feature_size, aligned_h: int, aligned_w: int, spatial_s
     nbytes = lib.tlod_roi_align_plan_bytes(B, R)
     plan = torch.empty((nbytes,), dtype=torch.uint8, device=rois.device)
     with torch.cuda.device(rois.device):
-        check(lib.tlod_roi_align_plan(rois.data_ptr(), B, H, W, R, int(aligned_h), int(aligned_w),
-                                      float(spatial_scale), plan.data_ptr(), plan.numel(), _stream(rois.device)),
-              "tlod_roi_align_plan")
+        rc = lib.tlod_roi_align_plan(rois.data_ptr(), B, H, W, R, int(aligned_h), int(aligned_w),
+                                     float(spatial_scale), plan.data_ptr(), plan.numel(), _stream(rois.device))
+    if rc == _lib.ERR_UNSUPPORTED:  # map too large for the planned kernels: the generic ones serve it
+        return None
+    check(rc, "tlod_roi_align_plan")
     return plan
 
 
@@ -103,6 +104,45 @@ def roi_align_backward(top_grad, rois, feature_size, spatial_scale: float, plan=
                                           AH, AW, float(spatial_scale), _ptr(plan),
                                           0 if plan is None else plan.numel(), _stream(top_grad.device)),
               "tlod_roi_align_backward")
+    return grad
+
+
+def roi_align_avg_forward(features, rois, pooled_h: int, pooled_w: int, spatial_scale: float, plan=None):
+    """RoIAlignAvg (modules/roi_align.py:20-29): samples at (pooled_h + 1, pooled_w + 1), 2x2 / stride-1
+    average -> (R, C, pooled_h, pooled_w).  7 x 7 with a plan is one kernel; the sample tensor never exists."""
+    _require_cuda(features, rois, plan)
+    features, rois = _f32(features), _f32(rois)
+    if rois.dim() != 2 or rois.size(1) != 5:
+        raise ValueError("rois must be (R, 5) [batch_idx, x1, y1, x2, y2]")
+    B, C, H, W = features.shape
+    R = rois.size(0)
+    out = torch.empty((R, C, pooled_h, pooled_w), dtype=torch.float32, device=features.device)
+    args = (features.data_ptr(), rois.data_ptr(), out.data_ptr(), B, C, H, W, R, int(pooled_h), int(pooled_w),
+            float(spatial_scale), _ptr(plan), 0 if plan is None else plan.numel())
+    with torch.cuda.device(features.device):
+        rc = lib.tlod_roi_align_avg_forward(*args, None, 0, _stream(features.device))
+        if rc == _lib.ERR_WORKSPACE:  # not the fused shape: the composed path needs the sample tensor
+            scratch = torch.empty((R, C, pooled_h + 1, pooled_w + 1), dtype=torch.float32, device=features.device)
+            rc = lib.tlod_roi_align_avg_forward(*args, scratch.data_ptr(), scratch.numel() * 4,
+                                                _stream(features.device))
+        check(rc, "tlod_roi_align_avg_forward")
+    return out
+
+
+def roi_align_avg_backward(top_grad, rois, feature_size, spatial_scale: float, plan=None):
+    """Adjoint of roi_align_avg_forward: (R, C, ph, pw) -> (B, C, H, W)."""
+    _require_cuda(top_grad, rois, plan)
+    top_grad, rois = _f32(top_grad), _f32(rois)
+    B, C, H, W = [int(v) for v in feature_size]
+    R, _, PH, PW = top_grad.shape
+    grad = torch.empty((B, C, H, W), dtype=torch.float32, device=top_grad.device)
+    scratch = torch.empty((R, C, PH + 1, PW + 1), dtype=torch.float32, device=top_grad.device)
+    with torch.cuda.device(top_grad.device):
+        check(lib.tlod_roi_align_avg_backward(top_grad.data_ptr(), rois.data_ptr(), grad.data_ptr(), B, C, H, W, R,
+                                              PH, PW, float(spatial_scale), _ptr(plan),
+                                              0 if plan is None else plan.numel(), scratch.data_ptr(),
+                                              max(scratch.numel() * 4, 4), _stream(top_grad.device)),
+              "tlod_roi_align_avg_backward")
     return grad
 
 
