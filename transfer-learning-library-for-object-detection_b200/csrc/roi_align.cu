@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(PL_THREADS)
     const int my_x = __shfl_sync(0xffffffffu, t.off, 16 + (lane & 7));
     if (lane < 8) {
       bc->cw0[lane] = my_cw0; bc->cw1[lane] = my_cw1; bc->ms[lane] = my_ms; bc->mh[lane] = my_mh;
-      bc->xoff[lane] = all_jump ? my_x * 4 : W * 4;
+      bc->xoff[lane] = (my_x < 0 ? 0 : my_x) * 4;  // invalid samples: cell 0 with zero weights
       const int t = lane + 1;
       const int ex = (t == 8) ? ex8 : ex_next;
       bc->soff[2 * lane] = ((en0 >> t) & 1u) ? ex * 4 : W * 4;  // W * 4: the dump cell

@@ -218,6 +218,27 @@ __global__ void __launch_bounds__(32 * F8_MAX_WARPS, 1)
       staged_slab = slab;
     }
 
+    // pull the slab this CTA stages next into L2 while this one is being gathered from
+    if (tid == 32 && bulk_stage) {
+      const long long un = u + (r_hi - r_lo);
+      if (un < u_end) {
+        const int cnt = __ldg(cum + img + 1) - __ldg(cum + img);
+        int ni = img, ns = slab + 1;  // the next unit is the next slab of this image, or the next image's first
+        if (r_hi < cnt) ns = slab;    // (same slab: nothing to fetch)
+        if (ns >= nslabs) {
+          ns = 0;
+          do { ++ni; } while (ni < B && __ldg(cum + ni + 1) == __ldg(cum + ni));
+        }
+        if (ni < B && (ni != img || ns != slab)) {
+          const unsigned char* g = reinterpret_cast<const unsigned char*>(features + ((size_t)ni * C + ns * F8_CH) * P);
+          const unsigned total = 64u * (unsigned)P;
+          for (unsigned done = 0; done < total; done += 32768u) {
+            const unsigned nb = total - done < 32768u ? total - done : 32768u;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g + done), "r"(nb) : "memory");
+          }
+        }
+      }
+    }
     const int base = __ldg(cum + img);
     int e = r_lo + wid;
     int n = (e < r_hi) ? __ldg(pl.list + base + e) : 0;
@@ -243,6 +264,10 @@ __global__ void __launch_bounds__(32 * F8_MAX_WARPS, 1)
         }
         __syncwarp();
 
+        // all table reads of the RoI are issued up front: the row loop below then never waits on one
+        float4 rt[8];
+#pragma unroll
+        for (int ph = 0; ph < 8; ++ph) rt[ph] = wtab[ph];
         unsigned ca[4], cb[4];
         float wp[4], wq[4];
 #pragma unroll
@@ -264,7 +289,7 @@ __global__ void __launch_bounds__(32 * F8_MAX_WARPS, 1)
         int prev = -100;
 #pragma unroll
         for (int ph = 0; ph < 8; ++ph) {
-          const float4 r = wtab[ph];
+          const float4 r = rt[ph];
           const int st = __float_as_int(r.w);
           float o[4] = {0.f, 0.f, 0.f, 0.f};
           if (st >= 0) {  // warp-uniform

@@ -20,7 +20,8 @@ constexpr int PL_MAXBINS = 8192;  // (image, plane row) bins of the backward row
 // predicates.
 struct __align__(16) BwdCols {
   float cw0[8], cw1[8];
-  int xoff[8];   // all-jump RoIs: byte offset of sample t's first cell (sites 2t, 2t+1 = xoff[t], xoff[t] + 4)
+  int xoff[8];   // byte offset of sample t's first cell in the row (0 with zero weights for an invalid
+                 // sample); all-jump RoIs: sites 2t, 2t+1 = xoff[t], xoff[t] + 4
   float ms[8], mh[8];
   int soff[16];  // site 2(t-1)+k (t = 1..8, k = 0/1): byte offset (ex[t] + k) * 4 in the row; width * 4 = dump
 };
