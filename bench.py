@@ -51,7 +51,7 @@ def peaks():
 
 def synth_inputs(seed, pin=False):
     """Host tensors of one rank's step (SURVEY.md 8d generators)."""
-    from oracle.synth import synth_gt, synth_rpn
+    from tools.synth import synth_gt, synth_rpn
     g = torch.Generator().manual_seed(seed)
     d = {}
     for dom, n in (("src", N_SRC), ("tgt", N_TGT)):
@@ -274,7 +274,7 @@ def parse_clocks(path):
 def roi_align_cfg3(dev, iters=20):
     """RoIAlign 8x8 forward and backward at BASELINE cfg3 (ResNet-101 conv4, batch 8, 256 RoIs/image):
     630 MB of algorithmic traffic per direction, larger than L2, so no flush is needed."""
-    from oracle.synth import synth_rois
+    from tools.synth import synth_rois
     from tlod_b200 import functional as F
     peak, peak_src = peaks()
     B, Cc, Hh, Ww, R = 8, 1024, 38, 75, 2048
@@ -328,7 +328,7 @@ def secondary_metrics(dev, iters=20):
     (12000 -> 2000 TRAIN, 6000 -> 300 TEST; proposal sets/s, proposals/s, fraction of the bound
     8(d) defines: max(bytes / HBM rate, 16 flop per upper-triangle pair / fp32 SIMT rate)), the
     cfg5 NMS sweep (batch x IoU threshold) and RoIPool forward + backward."""
-    from oracle.synth import synth_rois, synth_rpn
+    from tools.synth import synth_rois, synth_rpn
     from model.rpn.generate_anchors import generate_anchors
     from tlod_b200 import functional as F
     peak, _ = peaks()

@@ -351,6 +351,36 @@ int tlod_da_loss_backward(const float* img_score, const float* ins_prob, const f
                           float* grad_ins_prob, int batch, int height, int width, int num_ins,
                           void* stream);
 
+/* Image-level domain-classifier losses of up to TLOD_DA_MAX_LEVELS feature levels, one
+ * launch each way, any map size (multi-CTA, fp64 partial sums):
+ *   lib/MAF/faster_rcnn.py:188-205   conv3 / conv4 / conv5 heads,
+ *                                    F.nll_loss(F.log_softmax(score, 1), label) per level
+ *   lib/ATF/faster_rcnn.py:303-321   the same with ignore_index = -1
+ * The h_* arguments are HOST arrays of `levels` entries; h_scores[l] is the DEVICE pointer of
+ * level l's logits (h_batch[l], 2, h_height[l], h_width[l]); h_labels (may be NULL) holds per
+ * level the DEVICE pointer of an int64 label map (batch, height, width) -- what the reference's
+ * ImageLabelResizeLayer returns -- or NULL = every cell carries `domain_label`.  Cells whose
+ * label equals ignore_index are not counted.
+ * out (levels, 4) on the device: { mean NLL over the counted cells (NaN if none, like torch),
+ * mean softmax probability of class `domain_label` over them, number of counted cells, 0 }.
+ * The MAF instance-level CrossEntropyLoss over (R, 2) logits (faster_rcnn.py:207-213) is the
+ * same reduction with height = width = 1.
+ * Backward: grad_scores[l] = h_weights[l] * upstream[l] * d(out[l][0]) / d(score[l]), fully
+ * written (zeros at ignored cells); upstream: `levels` floats on the DEVICE or NULL (= 1),
+ * h_weights: host floats or NULL (= 1). */
+#define TLOD_DA_MAX_LEVELS 4
+size_t tlod_da_image_loss_workspace_bytes(void);
+int tlod_da_image_loss_forward(int levels, const float* const* h_scores,
+                               const long long* const* h_labels, const int* h_batch,
+                               const int* h_height, const int* h_width, int domain_label,
+                               int ignore_index, float* out, void* workspace, size_t workspace_bytes,
+                               void* stream);
+int tlod_da_image_loss_backward(int levels, const float* const* h_scores,
+                                const long long* const* h_labels, const int* h_batch,
+                                const int* h_height, const int* h_width, int domain_label,
+                                int ignore_index, const float* out, const float* upstream,
+                                const float* h_weights, float* const* h_grad_scores, void* stream);
+
 /* ------------------------------------------------------------------------ */
 /* RPN head losses                                         */
 /*   lib/model/rpn/rpn.py:90-108 (keep = label != -1, index_select,           */

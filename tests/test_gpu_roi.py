@@ -259,6 +259,11 @@ def test_roi_align_modules_and_autograd():
 
 POOL_CASES = {
     "vgg_conv5_7x7": (2, 32, 37, 75, 96, 7, 7, 1 / 16),
+    "res_conv4_7x7_many": (3, 64, 38, 75, 700, 7, 7, 1 / 16),      # plane-resident, several parts per unit
+    "one_image_few_rois": (1, 16, 37, 75, 9, 7, 7, 1 / 16),
+    "channels_x4_not_x16": (2, 20, 20, 31, 64, 7, 7, 1 / 16),       # generic forward, plane backward (NC = 4)
+    "odd_channels": (2, 7, 20, 31, 64, 7, 7, 1 / 16),               # NC = 1 backward
+    "cfg2_width": (2, 512, 37, 75, 512, 7, 7, 1 / 16),
     "pa_atf_conv3_stride4": (1, 8, 150, 300, 20, 7, 7, 1 / 4),
     "pa_atf_conv4_stride8": (1, 16, 75, 150, 20, 7, 7, 1 / 8),
     "odd_3x5": (3, 5, 13, 17, 40, 3, 5, 1 / 8),
@@ -280,6 +285,31 @@ def test_roi_pool_forward_backward(tag):
     refg = orc.roi_pool_backward(top.numpy(), ref_arg, rois.numpy(), feat.shape, scale)
     assert rel_err(grad, refg) <= 1e-4
     assert np.array_equal(grad == 0, refg == 0) or np.abs(grad[refg == 0]).max() < 1e-5
+
+
+def test_roi_pool_invalid_image_index_and_ties():
+    """RoIs with an image index outside [0, B) give 0 / -1; all-equal windows (ReLU zeros) pick the
+    first cell in row-major order; repeated launches are bit-identical in the forward."""
+    from tlod_b200 import functional as F
+    B, C, H, W, R, scale = 2, 32, 37, 75, 80, 1 / 16
+    feat = features(B, C, H, W, 91)
+    feat[:, ::2] = 0.0                       # whole planes of ties
+    feat[:, 1::4, 10:20, 30:50] = 1.0        # plateaus
+    rois = edge_rois(synth_rois(R, B, 92), H, W, scale)
+    rois[9, 0] = 5.0
+    rois[10, 0] = -1.0
+    out, arg = F.roi_pool_forward(feat.to(DEV), rois.to(DEV), 7, 7, scale)
+    keep = [i for i in range(R) if i not in (9, 10)]
+    ref, ref_arg = orc.roi_pool_forward(feat.numpy(), rois.numpy()[keep], 7, 7, scale)
+    assert bits_equal(out.cpu().numpy()[keep], ref)
+    assert np.array_equal(arg.cpu().numpy()[keep], ref_arg)
+    assert np.all(out.cpu().numpy()[[9, 10]] == 0) and np.all(arg.cpu().numpy()[[9, 10]] == -1)
+    out2, arg2 = F.roi_pool_forward(feat.to(DEV), rois.to(DEV), 7, 7, scale)
+    assert torch.equal(out, out2) and torch.equal(arg, arg2)
+    top = torch.randn(out.shape, generator=torch.Generator().manual_seed(93))
+    grad = F.roi_pool_backward(top.to(DEV), arg, rois.to(DEV), feat.shape, scale).cpu().numpy()
+    refg = orc.roi_pool_backward(top.numpy()[keep], ref_arg, rois.numpy()[keep], feat.shape, scale)
+    assert rel_err(grad, refg) <= 1e-4
 
 
 def test_roi_pool_module_autograd():

@@ -166,3 +166,59 @@ def test_da_losses_forward_backward(d):
     assert torch.allclose(cst, ref_cst, rtol=1e-5)
     assert torch.allclose(s.grad, s2.grad, rtol=1e-4, atol=1e-9)
     assert torch.allclose(p.grad, p2.grad, rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("d,batch", [(1, 1), (0, 8)])
+def test_image_da_losses_maf_three_levels(d, batch):
+    """MAF / PT-MAF: conv3 (B,2,150,300), conv4 (B,2,75,150), conv5 (B,2,37,75) heads in one launch
+    each way against the literal torch expressions of lib/MAF/faster_rcnn.py:188-205, including
+    the instance-level CrossEntropyLoss over (R, 2) logits (:207-213) as a fourth 'level'."""
+    import tlod_b200
+    g = torch.Generator().manual_seed(31 + d)
+    shapes = [(batch, 2, 150, 300), (batch, 2, 75, 150), (batch, 2, 37, 75), (256 * batch, 2, 1, 1)]
+    maps = [torch.randn(*s, generator=g) * 3 for s in shapes]
+    mine = [m.to(DEV).requires_grad_(True) for m in maps]
+    ref = [m.to(DEV).requires_grad_(True) for m in maps]
+    losses = tlod_b200.image_da_losses(mine, d)
+    ref_losses = []
+    for r in ref[:3]:
+        lab = torch.full((r.size(0), r.size(2), r.size(3)), d, dtype=torch.long, device=DEV)
+        ref_losses.append(torch.nn.functional.nll_loss(torch.log_softmax(r, 1), lab))
+    lab_ins = torch.full((ref[3].size(0),), d, dtype=torch.long, device=DEV)
+    ref_losses.append(torch.nn.CrossEntropyLoss()(ref[3].view(-1, 2), lab_ins))
+    for a, b in zip(losses, ref_losses):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-7)
+    w = torch.tensor([1.0, 0.5, 2.0, 0.1], device=DEV)
+    (losses * w).sum().backward()
+    sum(l * wi for l, wi in zip(ref_losses, w)).backward()
+    for a, b in zip(mine, ref):
+        assert torch.allclose(a.grad, b.grad, rtol=1e-4, atol=1e-10)
+
+
+def test_image_da_losses_atf_ignore_index():
+    """ATF: F.nll_loss(log_softmax(score, 1), label, ignore_index=-1) with label maps that mix
+    0 / 1 / -1 (lib/ATF/faster_rcnn.py:303-321); a level whose cells are all ignored gives NaN like torch."""
+    import tlod_b200
+    g = torch.Generator().manual_seed(41)
+    shapes = [(2, 2, 150, 300), (2, 2, 75, 150), (2, 2, 37, 75)]
+    maps = [torch.randn(*s, generator=g) for s in shapes]
+    labels = [torch.randint(-1, 2, (s[0], s[2], s[3]), generator=g) for s in shapes]
+    mine = [m.to(DEV).requires_grad_(True) for m in maps]
+    ref = [m.to(DEV).requires_grad_(True) for m in maps]
+    labs = [t.to(DEV) for t in labels]
+    losses = tlod_b200.image_da_losses(mine, 1, labs, ignore_index=-1)
+    ref_losses = [torch.nn.functional.nll_loss(torch.log_softmax(r, 1), t, ignore_index=-1) for r, t in zip(ref, labs)]
+    for a, b in zip(losses, ref_losses):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-7)
+    losses.sum().backward()
+    sum(ref_losses).backward()
+    for a, b in zip(mine, ref):
+        assert torch.allclose(a.grad, b.grad, rtol=1e-4, atol=1e-10)
+        assert torch.equal(a.grad == 0, b.grad == 0)  # ignored cells: exactly zero in both
+    # mixed: one level without a label map (domain label everywhere), one fully ignored
+    from tlod_b200 import functional as F
+    out = F.da_image_loss_forward([mine[2].detach(), mine[1].detach()], 0,
+                                  [None, torch.full_like(labs[1], -1)], ignore_index=-1)
+    lab0 = torch.zeros_like(labs[2])
+    assert torch.allclose(out[0, 0], torch.nn.functional.nll_loss(torch.log_softmax(ref[2].detach(), 1), lab0), rtol=1e-5)
+    assert torch.isnan(out[1, 0]) and out[1, 2].item() == 0

@@ -4,7 +4,7 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [os.path.join(ROOT, "transfer-learning-library-for-object-detection_b200"), ROOT]
 import numpy as np, torch
-from oracle.synth import synth_rpn
+from tools.synth import synth_rpn
 from tlod_b200 import functional as F, _lib
 from model.rpn.generate_anchors import generate_anchors
 dev = torch.device("cuda:0")

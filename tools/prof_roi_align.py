@@ -12,7 +12,7 @@ sys.path[:0] = [os.path.join(ROOT, "transfer-learning-library-for-object-detecti
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-from oracle.synth import synth_rois, synth_rpn  # noqa: E402
+from tools.synth import synth_rois, synth_rpn  # noqa: E402
 from tlod_b200 import functional as F  # noqa: E402
 from model.rpn.generate_anchors import generate_anchors  # noqa: E402
 

@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [os.path.join(ROOT, "transfer-learning-library-for-object-detection_b200"), ROOT]
 import torch  # noqa: E402
 
-from oracle.synth import synth_rois  # noqa: E402
+from tools.synth import synth_rois  # noqa: E402
 from tlod_b200 import functional as F  # noqa: E402
 
 dev = torch.device("cuda:0")

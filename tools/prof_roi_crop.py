@@ -3,7 +3,7 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [os.path.join(ROOT, "transfer-learning-library-for-object-detection_b200"), ROOT]
 import torch
-from oracle.synth import synth_rois
+from tools.synth import synth_rois
 from tlod_b200 import functional as F
 from model.utils.net_utils import _affine_grid_gen
 dev = torch.device("cuda:0")

@@ -3,7 +3,7 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [os.path.join(ROOT, "transfer-learning-library-for-object-detection_b200"), ROOT]
 import torch
-from oracle.synth import synth_rois
+from tools.synth import synth_rois
 from tlod_b200 import functional as F
 dev = torch.device("cuda:0")
 for (B, C, H, W, R) in ((2, 512, 37, 75, 512), (8, 1024, 38, 75, 2048)):

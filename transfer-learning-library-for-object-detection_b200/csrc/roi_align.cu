@@ -111,10 +111,15 @@ __global__ void __launch_bounds__(PL_THREADS)
   if (blockIdx.x == 0) {
     __shared__ int cnt[PL_MAXB + 2];
     __shared__ int next[PL_MAXB + 2];
-  
+    __shared__ int unsorted;
+    if (tid == 0) unsorted = 0;
     for (int i = tid; i <= B; i += PL_THREADS) cnt[i] = 0;
     __syncthreads();
-    for (int i = tid; i < R; i += PL_THREADS) atomicAdd(&cnt[roi_image(rois, i, B)], 1);
+    for (int i = tid; i < R; i += PL_THREADS) {
+      const int b = roi_image(rois, i, B);
+      atomicAdd(&cnt[b], 1);
+      if (i + 1 < R && roi_image(rois, i + 1, B) < b) unsorted = 1;
+    }
     __syncthreads();
     if (wid == 0) {
       int run = 0;
@@ -138,6 +143,10 @@ __global__ void __launch_bounds__(PL_THREADS)
       }
     }
     __syncthreads();
+    if (!unsorted) {  // RoIs already grouped by image (a proposal layer's output always is): identity
+      for (int i = tid; i < R; i += PL_THREADS) pl.list[i] = i;
+      return;
+    }
     for (int base = 0; base < R; base += PL_THREADS) {
       const int i = base + tid;
       const int b = (i < R) ? roi_image(rois, i, B) : -1 - tid;  // unique dummy keys

@@ -77,6 +77,9 @@ SIGNATURES = {
     "tlod_grl_backward_weighted": (c_int, [P, P, P, c_float, c_int, c_int, P]),
     "tlod_da_loss_workspace_bytes": (c_size_t, []),
     "tlod_da_loss_forward": (c_int, [P, P, P, c_int, P, c_int, c_int, c_int, c_int, P, c_size_t, P]),
+    "tlod_da_image_loss_workspace_bytes": (c_size_t, []),
+    "tlod_da_image_loss_forward": (c_int, [c_int, P, P, P, P, P, c_int, c_int, P, P, c_size_t, P]),
+    "tlod_da_image_loss_backward": (c_int, [c_int, P, P, P, P, P, c_int, c_int, P, P, P, P, P]),
     "tlod_da_loss_backward": (c_int, [P, P, P, c_int, P, P, c_float, c_float, c_float, P, P, c_int, c_int,
                                       c_int, c_int, P]),
 }

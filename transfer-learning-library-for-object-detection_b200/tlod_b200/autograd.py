@@ -181,3 +181,38 @@ class DALossFunction(Function):
 
 def da_losses(img_score, ins_prob, domain_label, ins_label=None):
     return DALossFunction.apply(img_score, ins_prob, domain_label, ins_label)
+
+
+class ImageDALossFunction(Function):
+    """Image-level DA losses of 1..4 feature levels (MAF's conv3 / conv4 / conv5 heads,
+    lib/MAF/faster_rcnn.py:188-205; ATF's ignore_index = -1, lib/ATF/faster_rcnn.py:303-321): one launch
+    forward, one backward.  Returns the (levels,) vector of mean NLLs; the reference adds them up."""
+
+    @staticmethod
+    def forward(ctx, domain_label, ignore_index, n_levels, *maps):
+        scores, labels = list(maps[:n_levels]), list(maps[n_levels:])
+        labels = labels if labels else None
+        out = F.da_image_loss_forward(scores, int(domain_label), labels, int(ignore_index))
+        ctx.save_for_backward(out, *scores, *([] if labels is None else [t for t in labels if t is not None]))
+        ctx.n = n_levels
+        ctx.has = None if labels is None else [t is not None for t in labels]
+        ctx.domain, ctx.ignore = int(domain_label), int(ignore_index)
+        return out[:, 0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        out, rest = ctx.saved_tensors[0], list(ctx.saved_tensors[1:])
+        scores, labs = rest[:ctx.n], rest[ctx.n:]
+        labels = None
+        if ctx.has is not None:
+            it = iter(labs)
+            labels = [next(it) if h else None for h in ctx.has]
+        grads = F.da_image_loss_backward(scores, ctx.domain, out, labels, ctx.ignore, upstream=g.contiguous().float())
+        return (None, None, None, *grads, *([None] * (0 if ctx.has is None else len(ctx.has))))
+
+
+def image_da_losses(scores, domain_label, labels=None, ignore_index=-100):
+    """scores: list of (B, 2, H, W) logits -> (levels,) mean NLL per level."""
+    scores = list(scores)
+    extra = [] if labels is None else list(labels)
+    return ImageDALossFunction.apply(int(domain_label), int(ignore_index), len(scores), *scores, *extra)

@@ -594,4 +594,55 @@ def da_loss_backward(img_score, ins_prob, domain_label: int, losses, w_img: floa
     return g_img, g_ins
 
 
+def _da_levels(scores, labels):
+    n = len(scores)
+    if not 1 <= n <= 4:
+        raise ValueError("1..4 feature levels")
+    scores = [_f32(s) for s in scores]
+    for s in scores:
+        if s.dim() != 4 or s.size(1) != 2:
+            raise ValueError("each score map must be (B, 2, H, W)")
+    labs = [None] * n if labels is None else [None if t is None else t.long().contiguous() for t in labels]
+    arr_p = (ctypes.c_void_p * n)
+    arr_i = (ctypes.c_int * n)
+    return (scores, labs, arr_p(*[s.data_ptr() for s in scores]), arr_p(*[_ptr(t) for t in labs]),
+            arr_i(*[s.size(0) for s in scores]), arr_i(*[s.size(2) for s in scores]),
+            arr_i(*[s.size(3) for s in scores]))
+
+
+def da_image_loss_forward(scores, domain_label: int, labels=None, ignore_index: int = -100):
+    """Image-level DA losses of 1..4 feature levels in one launch (MAF conv3/conv4/conv5 heads, ATF's
+    ignore_index = -1).  scores: list of (B, 2, H, W) logits; labels: None (= domain_label everywhere) or a
+    list of int64 (B, H, W) maps / None per level.  -> (levels, 4) device tensor
+    [nll mean, mean softmax prob of class domain_label, counted cells, 0] per level."""
+    _require_cuda(*scores)
+    scores, labs, sp, lp, bb, hh, ww = _da_levels(scores, labels)
+    dev = scores[0].device
+    out = torch.empty((len(scores), 4), dtype=torch.float32, device=dev)
+    ws = _workspace(dev, lib.tlod_da_image_loss_workspace_bytes(), "da_image")
+    with torch.cuda.device(dev):
+        check(lib.tlod_da_image_loss_forward(len(scores), sp, lp, bb, hh, ww, int(domain_label), int(ignore_index),
+                                             out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)),
+              "tlod_da_image_loss_forward")
+    return out
+
+
+def da_image_loss_backward(scores, domain_label: int, out, labels=None, ignore_index: int = -100, upstream=None,
+                           weights=None):
+    """-> list of gradients w.r.t. each level's score map (of weights[l] * upstream[l] * loss[l])."""
+    _require_cuda(*scores)
+    scores, labs, sp, lp, bb, hh, ww = _da_levels(scores, labels)
+    n = len(scores)
+    dev = scores[0].device
+    grads = [torch.empty_like(s) for s in scores]
+    gp = (ctypes.c_void_p * n)(*[g.data_ptr() for g in grads])
+    up = None if upstream is None else _f32(upstream)
+    wt = None if weights is None else (ctypes.c_float * n)(*[float(w) for w in weights])
+    with torch.cuda.device(dev):
+        check(lib.tlod_da_image_loss_backward(n, sp, lp, bb, hh, ww, int(domain_label), int(ignore_index),
+                                              out.data_ptr(), _ptr(up), wt, gp, _stream(dev)),
+              "tlod_da_image_loss_backward")
+    return grads
+
+
 launch_count = _lib.launch_count
