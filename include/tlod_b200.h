@@ -174,6 +174,33 @@ int tlod_roi_crop_backward(const float* grad_output, const float* grid_yx, float
                            int in_batch, int channels, int height, int width, int out_batch,
                            int grid_h, int grid_w, void* stream);
 
+/* RoICrop on an axis-aligned grid fused with the max_pool2d(2, 2) that follows it in the
+ * detector (cfg.POOLING_MODE == 'crop': lib/model/faster_rcnn/faster_rcnn.py:73-80,
+ * _affine_grid_gen lib/model/utils/net_utils.py:142-164): the (out_batch, C, 14, 14) sample
+ * tensor is never written.  The rotation-free affine grid is the outer product of per-RoI
+ * coordinate vectors: grid_y (out_batch, grid_h) and grid_x (out_batch, grid_w), normalised
+ * to [-1, 1] exactly like the (y, x) grid of tlod_roi_crop_forward (grid[n, i, j] =
+ * (grid_y[n, i], grid_x[n, j])); RoI n samples image n / (out_batch / in_batch).
+ * output (out_batch, C, grid_h / 2, grid_w / 2); argmax (same shape, uint8, may be NULL in
+ * the forward): which sample of the 2 x 2 window won, 2 * dy + dx, first maximum in row-major
+ * order (max_pool2d's rule) -- the backward routes the gradient through it.
+ * Implemented for grid_h == grid_w == 14 (the reference's POOLING_SIZE * 2), channels % 16 == 0
+ * and maps whose 16 planes fit shared memory; anything else returns TLOD_ERR_UNSUPPORTED with
+ * nothing launched (compose tlod_roi_crop_forward and a pooling pass instead).
+ * workspace: tlod_roi_crop_pool_workspace_bytes(out_batch), 16-byte aligned; it holds the
+ * per-RoI sampling tables and may be discarded after each call.
+ * Backward: grad_features (in_batch, C, H, W) is fully overwritten. */
+size_t tlod_roi_crop_pool_workspace_bytes(int out_batch);
+int tlod_roi_crop_pool_forward(const float* features, const float* grid_y, const float* grid_x,
+                               float* output, unsigned char* argmax, int in_batch, int channels,
+                               int height, int width, int out_batch, int grid_h, int grid_w,
+                               void* workspace, size_t workspace_bytes, void* stream);
+int tlod_roi_crop_pool_backward(const float* grad_output, const unsigned char* argmax,
+                                const float* grid_y, const float* grid_x, float* grad_features,
+                                int in_batch, int channels, int height, int width, int out_batch,
+                                int grid_h, int grid_w, void* workspace, size_t workspace_bytes,
+                                void* stream);
+
 /* ------------------------------------------------------------------------ */
 /* NMS                                                                        */
 /* replaces nms_cuda                lib/model/nms/src/nms_cuda.c:8-19         */

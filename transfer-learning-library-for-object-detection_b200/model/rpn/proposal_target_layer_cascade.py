@@ -21,30 +21,43 @@ class _ProposalTargetLayer(nn.Module):
     def __init__(self, nclasses):
         super(_ProposalTargetLayer, self).__init__()
         self._num_classes = nclasses
-        self._host = None
 
     def forward(self, all_rois, gt_boxes, num_boxes):
-        B, K = gt_boxes.size(0), gt_boxes.size(1)
-        dev = gt_boxes.device
+        state = self.begin(all_rois, gt_boxes, num_boxes)
+        keep, fg_count = self.sample(state)
+        return self.finish(state, keep, fg_count)
+
+    # forward() = finish(sample(begin())).  The three parts exist so that a caller can overlap other
+    # GPU work with the host-side sampling, or capture the device parts in CUDA graphs:
+    #   begin()  launches only: candidate assembly, tlod_roi_gt_assign, a pinned D2H copy + event;
+    #   sample() waits for that event alone and draws the fg / bg samples on the host (numpy RNG);
+    #   finish() uploads the sampled indices and launches tlod_proposal_targets.
+    def begin(self, all_rois, gt_boxes, num_boxes, host=None):
         # :42-46 -- ground-truth boxes join the candidates (class column dropped, image index 0)
         gt_append = gt_boxes.new_zeros(gt_boxes.size())
         gt_append[:, :, 1:5] = gt_boxes[:, :, :4]
         all_rois = torch.cat([all_rois, gt_append], 1).contiguous()
-        n = all_rois.size(1)
+        max_overlaps, assignment, labels = F.roi_gt_assign(all_rois, gt_boxes)
+        if host is None:
+            host = torch.empty(max_overlaps.shape, dtype=torch.float32).pin_memory()
+        host.copy_(max_overlaps, non_blocking=True)
+        copied = None
+        if not torch.cuda.is_current_stream_capturing():
+            copied = torch.cuda.Event()
+            copied.record(torch.cuda.current_stream(gt_boxes.device))
+        return {"all_rois": all_rois, "gt_boxes": gt_boxes, "assignment": assignment, "labels": labels,
+                "host": host, "copied": copied}
 
+    def sample(self, state):
+        """Host-side fg / bg sampling, :140-181: same index order, same RNG calls."""
+        if state["copied"] is not None:
+            state["copied"].synchronize()
+        mo = state["host"].numpy()
+        B = mo.shape[0]
         num_images = 1
         rois_per_image = int(cfg.TRAIN.BATCH_SIZE / num_images)
         fg_rois_per_image = int(np.round(cfg.TRAIN.FG_FRACTION * rois_per_image))
         fg_rois_per_image = 1 if fg_rois_per_image == 0 else fg_rois_per_image
-
-        max_overlaps, assignment, labels = F.roi_gt_assign(all_rois, gt_boxes)
-        if self._host is None or self._host.shape != max_overlaps.shape:
-            self._host = torch.empty(max_overlaps.shape, dtype=torch.float32).pin_memory()
-        self._host.copy_(max_overlaps, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
-        mo = self._host.numpy()
-
-        # ---- host-side sampling, :140-181: same index order, same RNG calls ----
         keep = np.empty((B, rois_per_image), np.int32)
         fg_count = np.empty((B,), np.int32)
         fg_thresh = np.float32(cfg.TRAIN.FG_THRESH)
@@ -74,14 +87,18 @@ class _ProposalTargetLayer(nn.Module):
                 raise ValueError("bg_num_rois = 0 and fg_num_rois = 0, this should not happen!")
             keep[i] = np.concatenate([fg_inds, bg_inds])
             fg_count[i] = fg_this
+        return keep, fg_count
 
-        keep_d = torch.from_numpy(keep).to(dev, non_blocking=True)
-        fg_d = torch.from_numpy(fg_count).to(dev, non_blocking=True)
-        rois, labels_b, targets, inside, outside = F.proposal_targets(
-            all_rois, gt_boxes, assignment, labels, keep_d, fg_d, cfg.TRAIN.BBOX_NORMALIZE_MEANS,
-            cfg.TRAIN.BBOX_NORMALIZE_STDS, cfg.TRAIN.BBOX_INSIDE_WEIGHTS,
+    def finish(self, state, keep, fg_count):
+        """keep (B, rois_per_image) / fg_count (B,): numpy arrays from sample(), or int32 device tensors
+        that already hold them (a caller replaying a captured graph uploads into static buffers)."""
+        dev = state["gt_boxes"].device
+        keep_d = keep if torch.is_tensor(keep) else torch.from_numpy(keep).to(dev, non_blocking=True)
+        fg_d = fg_count if torch.is_tensor(fg_count) else torch.from_numpy(fg_count).to(dev, non_blocking=True)
+        return F.proposal_targets(
+            state["all_rois"], state["gt_boxes"], state["assignment"], state["labels"], keep_d, fg_d,
+            cfg.TRAIN.BBOX_NORMALIZE_MEANS, cfg.TRAIN.BBOX_NORMALIZE_STDS, cfg.TRAIN.BBOX_INSIDE_WEIGHTS,
             cfg.TRAIN.BBOX_NORMALIZE_TARGETS_PRECOMPUTED)
-        return rois, labels_b, targets, inside, outside
 
     def backward(self, top, propagate_down, bottom):
         """This layer does not propagate gradients."""

@@ -32,3 +32,19 @@ def roi_crop_pool(roi_crop, base_feat, rois, grid_size):
     grid_xy = _affine_grid_gen(rois.view(-1, 5), base_feat.size()[2:], grid_size)
     grid_yx = torch.stack([grid_xy[:, :, :, 1], grid_xy[:, :, :, 0]], 3).contiguous()
     return roi_crop(base_feat, grid_yx.detach())
+
+
+def roi_crop_max_pool(base_feat, rois, grid_size):
+    """The whole 'crop' branch (faster_rcnn.py:73-80) -- affine grid, RoICrop, F.max_pool2d(., 2, 2) --
+    as ONE kernel each way when cfg.CROP_RESIZE_WITH_MAX_POOL doubles the grid to 14: the
+    (R, C, 14, 14) sample tensor is never written.  Other sizes compose RoICrop and torch's pooling."""
+    from tlod_b200 import functional as TF
+    from tlod_b200.autograd import RoICropFunction, RoICropPoolFunction
+    grid_xy = _affine_grid_gen(rois.view(-1, 5), base_feat.size()[2:], grid_size)
+    if TF.roi_crop_pool_supported(base_feat, grid_size, grid_size):
+        # rotation-free theta: the grid is the outer product of its first column (y) and first row (x)
+        grid_y = grid_xy[:, :, 0, 1].contiguous()
+        grid_x = grid_xy[:, 0, :, 0].contiguous()
+        return RoICropPoolFunction.apply(base_feat, grid_y.detach(), grid_x.detach())
+    grid_yx = torch.stack([grid_xy[:, :, :, 1], grid_xy[:, :, :, 0]], 3).contiguous()
+    return F.max_pool2d(RoICropFunction.apply(base_feat, grid_yx.detach()), 2, 2)

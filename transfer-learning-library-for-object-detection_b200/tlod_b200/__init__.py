@@ -10,9 +10,9 @@ from . import _lib  # noqa: F401  (raises if libtlod_b200.so is missing)
 from . import functional  # noqa: F401
 from . import sharding  # noqa: F401
 from .autograd import (DALossFunction, ImageDALossFunction, image_da_losses, GradReverse, RoIAlignAvgFunction, RoIAlignFunction,  # noqa: F401
-                       RoICropFunction, RoIPoolFunction, RPNLossFunction, SpaceToDepthFunction, da_losses, rpn_losses, space_to_depth,
+                       RoICropFunction, RoICropPoolFunction, RoIPoolFunction, RPNLossFunction, SpaceToDepthFunction, da_losses, rpn_losses, space_to_depth,
                        grad_reverse)
 from ._lib import TlodError, launch_count  # noqa: F401
 
-__all__ = ["functional", "RoIAlignFunction", "RoIAlignAvgFunction", "RoICropFunction", "RoIPoolFunction", "GradReverse", "grad_reverse", "DALossFunction",
+__all__ = ["functional", "RoIAlignFunction", "RoIAlignAvgFunction", "RoICropFunction", "RoICropPoolFunction", "RoIPoolFunction", "GradReverse", "grad_reverse", "DALossFunction",
            "da_losses", "ImageDALossFunction", "image_da_losses", "RPNLossFunction", "rpn_losses", "SpaceToDepthFunction", "space_to_depth", "TlodError", "launch_count"]

@@ -41,6 +41,11 @@ SIGNATURES = {
     "tlod_roi_pool_backward": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P]),
     "tlod_roi_crop_forward": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "tlod_roi_crop_backward": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "tlod_roi_crop_pool_workspace_bytes": (c_size_t, [c_int]),
+    "tlod_roi_crop_pool_forward": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P,
+                                           c_size_t, P]),
+    "tlod_roi_crop_pool_backward": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P,
+                                            c_size_t, P]),
     "tlod_nms_workspace_bytes": (c_size_t, [c_int]),
     "tlod_nms": (c_int, [P, c_int, c_int, c_float, c_int, P, P, P, c_size_t, P]),
     "tlod_class_nms_padded_rows": (c_int, [c_int]),

@@ -93,6 +93,23 @@ class RoICropFunction(Function):
         return F.roi_crop_backward(grad_output, grid, ctx.feature_size), torch.zeros_like(grid)
 
 
+class RoICropPoolFunction(Function):
+    """RoICrop on the rotation-free affine grid of _affine_grid_gen + F.max_pool2d(., 2, 2) as one node
+    (lib/model/faster_rcnn/faster_rcnn.py:73-80).  grid_y / grid_x (R, 14): row / column coordinates."""
+
+    @staticmethod
+    def forward(ctx, features, grid_y, grid_x):
+        out, arg = F.roi_crop_pool_forward(features, grid_y, grid_x)
+        ctx.save_for_backward(arg, grid_y, grid_x)
+        ctx.feature_size = tuple(features.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        arg, grid_y, grid_x = ctx.saved_tensors
+        return F.roi_crop_pool_backward(grad_output, arg, grid_y, grid_x, ctx.feature_size), None, None
+
+
 class GradReverse(Function):
     """Identity forward; backward -alpha * g (optionally * per-row weight, lib/MAF/DA.py:34-53)."""
 

@@ -229,6 +229,48 @@ def roi_crop_backward(grad_output, grid_yx, feature_size):
     return grad
 
 
+def roi_crop_pool_supported(features, grid_h: int, grid_w: int) -> bool:
+    """Shapes served by the fused RoICrop + max_pool2d(2, 2) kernels (the C side re-checks)."""
+    return grid_h == 14 and grid_w == 14 and features.size(1) % 16 == 0 and \
+        features.size(2) * features.size(3) * 64 <= 190 * 1024
+
+
+def roi_crop_pool_forward(features, grid_y, grid_x):
+    """RoICrop on the axis-aligned grid (grid_y (R, 14), grid_x (R, 14)) + max_pool2d(2, 2) in one kernel:
+    -> (pooled (R, C, 7, 7), argmax (R, C, 7, 7) uint8)."""
+    _require_cuda(features, grid_y, grid_x)
+    features, grid_y, grid_x = _f32(features), _f32(grid_y), _f32(grid_x)
+    ib, C, H, W = features.shape
+    ob, GH = grid_y.shape
+    GW = grid_x.size(1)
+    dev = features.device
+    out = torch.empty((ob, C, GH // 2, GW // 2), dtype=torch.float32, device=dev)
+    arg = torch.empty((ob, C, GH // 2, GW // 2), dtype=torch.uint8, device=dev)
+    ws = _workspace(dev, lib.tlod_roi_crop_pool_workspace_bytes(ob), "crop_pool")
+    with torch.cuda.device(dev):
+        check(lib.tlod_roi_crop_pool_forward(features.data_ptr(), grid_y.data_ptr(), grid_x.data_ptr(),
+                                             out.data_ptr(), arg.data_ptr(), ib, C, H, W, ob, GH, GW, ws.data_ptr(),
+                                             ws.numel(), _stream(dev)), "tlod_roi_crop_pool_forward")
+    return out, arg
+
+
+def roi_crop_pool_backward(grad_output, argmax, grid_y, grid_x, feature_size):
+    _require_cuda(grad_output, argmax, grid_y, grid_x)
+    grad_output, grid_y, grid_x = _f32(grad_output), _f32(grid_y), _f32(grid_x)
+    ib, C, H, W = [int(v) for v in feature_size]
+    ob, GH = grid_y.shape
+    GW = grid_x.size(1)
+    dev = grad_output.device
+    grad = torch.empty((ib, C, H, W), dtype=torch.float32, device=dev)
+    ws = _workspace(dev, lib.tlod_roi_crop_pool_workspace_bytes(ob), "crop_pool")
+    with torch.cuda.device(dev):
+        check(lib.tlod_roi_crop_pool_backward(grad_output.data_ptr(), argmax.contiguous().data_ptr(),
+                                              grid_y.data_ptr(), grid_x.data_ptr(), grad.data_ptr(), ib, C, H, W, ob,
+                                              GH, GW, ws.data_ptr(), ws.numel(), _stream(dev)),
+              "tlod_roi_crop_pool_backward")
+    return grad
+
+
 # ---------------------------------------------------------------------------
 # NMS / proposals
 # ---------------------------------------------------------------------------
