@@ -4,15 +4,16 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...   # reference CPU path (oracle port)
 
-Workload (BASELINE.json configs[1]), per GPU: one DAF-style
-training step's operator sequence on 2 source + 2 target synthetic 600x1200 images
-(VGG16 conv5 maps 512x37x75, A = 12 anchors):
-  source: proposal layer TRAIN (12000 -> 2000, NMS 0.7), anchor targets, RoIAlignAvg 7x7
-          forward + backward on 256 RoIs/image, image/instance DA losses fwd+bwd, GRL;
-  target: proposal layer TEST (6000 -> 300), RoIAlignAvg forward + backward on 300
-          RoIs/image, DA losses fwd+bwd, GRL.
-`value` = RoIs pooled forward+backward per second over the whole step, all GPUs
-(weak scaling: every rank runs its own 4 images; there is no collective on the path).
+Workload (BASELINE.json configs[1]), per GPU: the operator sequence of one DAF
+training step on 2 source + 2 target synthetic 600x1200 images (VGG16 conv5 maps 512x37x75, A = 12):
+  source: proposal layer TRAIN (12000 -> 2000, NMS 0.7) -> _ProposalTargetLayer (IoU, host-RNG
+          fg/bg sampling of 256 RoIs/image, regression targets) -> RoIAlignAvg 7x7 forward +
+          backward, anchor-target layer -> RPN cls / box losses forward + backward,
+          image / instance / consistency DA losses forward + backward, GRL;
+  target: proposal layer TEST (6000 -> 300) -> RoIAlignAvg forward + backward on 300 RoIs/image,
+          DA losses forward + backward, GRL.
+`value` = RoIs pooled forward+backward per second over the whole step, all GPUs (weak scaling:
+every rank runs its own 4 images; there is no collective on the path).
 """
 import argparse
 import json
@@ -32,13 +33,30 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 C, H, W, A = 512, 37, 75, 12
-N_SRC, N_TGT = 2, 2
 ROIS_SRC, ROIS_TGT = 256, 300
-ROIS_PER_STEP = N_SRC * ROIS_SRC + N_TGT * ROIS_TGT
-PROPOSALS_PER_STEP = N_SRC * 2000 + N_TGT * 300
-WORKLOAD = ("cfg2: DAF VGG16 step ops, 2 src + 2 tgt 600x1200 images/GPU, conv5 512x37x75, "
-            "RPN 12000->2000 (src) / 6000->300 (tgt) NMS 0.7, RoIAlignAvg 7x7 fwd+bwd on 256/300 RoIs per image, "
-            "anchor targets, image+instance DA losses, GRL")
+METRIC = "RoIs/sec RoIAlign fwd+bwd & proposals/sec (12000->2000 NMS) vs HBM roofline"
+
+
+class Workload(object):
+    """cfg2: the DAF step (2 + 2 images).  cfg4: 4 + 4 images per GPU with the MAF multi-level domain
+    classifiers (conv3 / conv4 / conv5 image heads, instance cross-entropy, weighted GRL)."""
+
+    def __init__(self, name):
+        self.name = name
+        self.maf = name == "cfg4"
+        self.n_src = self.n_tgt = 4 if self.maf else 2
+        self.rois_per_step = self.n_src * ROIS_SRC + self.n_tgt * ROIS_TGT
+        self.proposals_per_step = self.n_src * 2000 + self.n_tgt * 300
+        if self.maf:
+            self.text = ("cfg4: MAF step ops, 4 src + 4 tgt 600x1200 images/GPU, conv5 512x37x75, RPN 12000->2000 / "
+                         "6000->300 NMS 0.7, proposal targets, RoIAlignAvg 7x7 fwd+bwd on 256/300 RoIs per image, "
+                         "anchor targets + RPN losses, image DA heads at conv3 (2x150x300) / conv4 (2x75x150) / "
+                         "conv5 (2x37x75), instance cross-entropy, weighted GRL")
+        else:
+            self.text = ("cfg2: DAF VGG16 step ops, 2 src + 2 tgt 600x1200 images/GPU, conv5 512x37x75, "
+                         "RPN 12000->2000 (src) / 6000->300 (tgt) NMS 0.7, proposal targets (256 RoIs/image), "
+                         "RoIAlignAvg 7x7 fwd+bwd on 256/300 RoIs per image, anchor targets + RPN losses, "
+                         "image+instance DA losses, GRL")
 
 
 def peaks():
@@ -49,12 +67,12 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def synth_inputs(seed, pin=False):
+def synth_inputs(seed, wl):
     """Host tensors of one rank's step (SURVEY.md 8d generators)."""
     from tools.synth import synth_gt, synth_rpn
     g = torch.Generator().manual_seed(seed)
     d = {}
-    for dom, n in (("src", N_SRC), ("tgt", N_TGT)):
+    for dom, n in (("src", wl.n_src), ("tgt", wl.n_tgt)):
         d[dom + "_feat"] = torch.relu(torch.randn(n, C, H, W, generator=g))
         prob, deltas = synth_rpn(n, A, H, W, seed + (1 if dom == "src" else 2))
         d[dom + "_prob"], d[dom + "_deltas"] = prob, deltas
@@ -62,182 +80,319 @@ def synth_inputs(seed, pin=False):
         d[dom + "_img_score"] = torch.randn(n, 2, H, W, generator=g)
         r = n * (ROIS_SRC if dom == "src" else ROIS_TGT)
         d[dom + "_ins_prob"] = torch.sigmoid(torch.randn(r, 1, generator=g))
-    d["src_gt"] = synth_gt(N_SRC, 20, 50, seed + 50)
-    if pin:
-        d = {k: v.pin_memory() for k, v in d.items()}
+        if wl.maf:
+            d[dom + "_img_score3"] = torch.randn(n, 2, 150, 300, generator=g)
+            d[dom + "_img_score4"] = torch.randn(n, 2, 75, 150, generator=g)
+            d[dom + "_ins_logit"] = torch.randn(r, 2, generator=g)
+    # RPN head outputs of the source images (logits; the proposal layer gets their softmax above)
+    d["src_rpn_cls"] = 2.0 * torch.randn(wl.n_src, 2 * A, H, W, generator=g)
+    d["src_rpn_box"] = 0.2 * torch.randn(wl.n_src, 4 * A, H, W, generator=g)
+    d["src_gt"] = synth_gt(wl.n_src, 20, 50, seed + 50)
     return d
+
+
+class Arena(object):
+    """One pinned host buffer and one device buffer holding a group of tensors back to back: a
+    whole group crosses PCIe with ONE copy (bench e2e mode)."""
+
+    def __init__(self, tensors, dev, to_device):
+        self.names = list(tensors)
+        sizes = [(tensors[k].numel() * 4 + 255) // 256 * 256 for k in self.names]
+        total = sum(sizes)
+        self.host = torch.empty(total, dtype=torch.uint8).pin_memory()
+        self.dev = torch.empty(total, dtype=torch.uint8, device=dev)
+        self.hviews, self.dviews = {}, {}
+        off = 0
+        for k, sz in zip(self.names, sizes):
+            t = tensors[k]
+            n = t.numel() * 4
+            self.hviews[k] = self.host[off:off + n].view(torch.float32).view(t.shape)
+            self.dviews[k] = self.dev[off:off + n].view(torch.float32).view(t.shape)
+            if to_device:
+                self.hviews[k].copy_(t)
+            off += sz
+        self.nbytes = total
+        if to_device:
+            self.dev.copy_(self.host)
+
+    def h2d(self):
+        self.dev.copy_(self.host, non_blocking=True)
+
+    def d2h(self):
+        self.host.copy_(self.dev, non_blocking=True)
 
 
 # ---------------------------------------------------------------------------
 # this repo's arm
 # ---------------------------------------------------------------------------
 class TlodStep(object):
-    """One rank's step.  The device-only part (proposal layers, RoIAlignAvg forward + backward, DA
-    losses, GRL for both domains: ~45 launches, static shapes, no host synchronisation anywhere)
-    is captured once into a CUDA graph and replayed; the anchor-target layer follows eagerly
-    because its subsampling consumes numpy's host RNG exactly like the reference."""
+    """One rank's step.  Device work without a host dependency is captured in three CUDA graphs:
+      src1: proposal layer TRAIN, candidate assembly, IoU/assignment, pinned D2H of the overlaps
+      src2: proposal targets, RoIAlignAvg fwd + bwd, GRL                 (after the host's fg / bg sampling)
+      src3: DA losses fwd + bwd, RPN losses fwd + bwd                    (after the anchor-target layer)
+      tgt : proposal layer TEST, RoIAlignAvg fwd + bwd, DA losses fwd + bwd, GRL
+    The host part -- the anchor-target layer's subsampling, then the fg / bg sampling of the proposal
+    targets, in the reference's order on numpy's RNG stream -- runs while the GPU works through
+    src1 / tgt; it is the longest chain of the step."""
 
-    def __init__(self, dev, seed, use_graph=True):
+    def __init__(self, dev, seed, wl, use_graph=True):
         from model.roi_align.modules.roi_align import RoIAlignAvg
         from model.rpn.anchor_target_layer import _AnchorTargetLayer
         from model.rpn.proposal_layer import _ProposalLayer
+        from model.rpn.proposal_target_layer_cascade import _ProposalTargetLayer
+        from model.utils.config import cfg
         import tlod_b200
         self.tlod = tlod_b200
         self.dev = dev
-        self.host = synth_inputs(seed, pin=True)
-        self.d = {k: v.to(dev) for k, v in self.host.items()}
+        self.wl = wl
+        cfg.TRAIN.BATCH_SIZE = ROIS_SRC  # cfgs/vgg16.yml
+        host = synth_inputs(seed, wl)
+        # inputs in two arenas (one H2D copy per domain in e2e mode)
+        self.arena = {dom: Arena({k: v for k, v in host.items() if k.startswith(dom)}, dev, True)
+                      for dom in ("src", "tgt")}
+        self.d = {}
+        for a in self.arena.values():
+            self.d.update(a.dviews)
         self.proposal = _ProposalLayer(16, [4, 8, 16, 32], [0.5, 1, 2])
         self.anchor_target = _AnchorTargetLayer(16, [4, 8, 16, 32], [0.5, 1, 2])
+        self.proposal_target = _ProposalTargetLayer(9)
         self.roi_align = RoIAlignAvg(7, 7, 1.0 / 16.0)
         g = torch.Generator().manual_seed(seed + 99)
         # gradient arriving from the detection head: device resident (it never exists on the host)
-        self.top = {"src": torch.randn(N_SRC * ROIS_SRC, C, 7, 7, generator=g).to(dev),
-                    "tgt": torch.randn(N_TGT * ROIS_TGT, C, 7, 7, generator=g).to(dev)}
-        self.num_boxes = torch.full((N_SRC,), 20, dtype=torch.long)
-        np.random.seed(3)
-        self.graph = None
+        self.top = {"src": torch.randn(wl.n_src * ROIS_SRC, C, 7, 7, generator=g).to(dev),
+                    "tgt": torch.randn(wl.n_tgt * ROIS_TGT, C, 7, 7, generator=g).to(dev)}
+        if wl.maf:
+            self.cls_prob = {dom: torch.softmax(torch.randn(r, 9, generator=g), 1).to(dev)
+                             for dom, r in (("src", wl.n_src * ROIS_SRC), ("tgt", wl.n_tgt * ROIS_TGT))}
+            self.pooled_grad = {dom: torch.randn(r, 4096, generator=g).to(dev)
+                                for dom, r in (("src", wl.n_src * ROIS_SRC), ("tgt", wl.n_tgt * ROIS_TGT))}
+        self.num_boxes = torch.full((wl.n_src,), 20, dtype=torch.long)
+        self.streams = {k: torch.cuda.Stream(dev) for k in ("src", "tgt", "side")}
+        # static buffers of the proposal-target hand-over (graph mode replays into / out of them)
+        self.pt_host = torch.empty((wl.n_src, 2000 + 50), dtype=torch.float32).pin_memory()
+        self.keep_d = torch.zeros((wl.n_src, ROIS_SRC), dtype=torch.int32, device=dev)
+        self.fg_d = torch.zeros((wl.n_src,), dtype=torch.int32, device=dev)
+        self.keep_h = torch.zeros((wl.n_src, ROIS_SRC), dtype=torch.int32).pin_memory()
+        self.fg_h = torch.zeros((wl.n_src,), dtype=torch.int32).pin_memory()
+        self.at_static = None
+        self.at_host = None
         self.graphs = None
-        self.static = None
-        self.streams = None
+        self.static = {}
         self.launches_per_replay = 0
-        self.host_out = None
-        self.side = None
+        self.out_arena = None
+        np.random.seed(3)
         if use_graph:
             self.capture()
 
-    def domain(self, dom, d, results):
-        key = "TRAIN" if dom == "src" else "TEST"
-        per = ROIS_SRC if dom == "src" else ROIS_TGT
-        feat = d[dom + "_feat"].requires_grad_(True)
-        rois = self.proposal((d[dom + "_prob"], d[dom + "_deltas"], d[dom + "_im_info"], key))
-        sel = rois[:, :per, :].reshape(-1, 5)  # stand-in for _ProposalTargetLayer's sampling
-        pooled = self.roi_align(feat, sel)
+    # ---- the pieces (each only enqueues work on the current stream) ----
+    def da_part(self, dom, d, pooled_rois):
+        """Domain-classifier losses forward + backward and the GRLs in front of the heads."""
+        dl = 1 if dom == "src" else 0
         score = d[dom + "_img_score"].requires_grad_(True)
+        if self.wl.maf:
+            s3 = d[dom + "_img_score3"].requires_grad_(True)
+            s4 = d[dom + "_img_score4"].requires_grad_(True)
+            ins = d[dom + "_ins_logit"].requires_grad_(True)
+            losses = self.tlod.image_da_losses([s3, s4, score, ins.view(-1, 2, 1, 1)], dl)
+            (0.1 * losses.sum()).backward()
+            # weighted GRL in front of the instance head (lib/MAF/DA.py:34-53): -0.2 * g * cls_prob[:, dc_label]
+            g_ins = self.tlod.functional.grl_backward(self.pooled_grad[dom], 0.2, self.cls_prob[dom][:, dl].contiguous())
+            out = (losses.detach(), score.grad, s3.grad, s4.grad, ins.grad, g_ins)
+            for t in (score, s3, s4, ins):
+                t.grad = None
+            return out
         prob = d[dom + "_ins_prob"].requires_grad_(True)
-        img, ins, cst = self.tlod.da_losses(score, prob, 1 if dom == "src" else 0)
-        loss = 0.1 * (img + ins + cst)
-        torch.autograd.backward([pooled, loss], [self.top[dom], None])
-        # GRL in front of the DA heads: base_feat gradient and pooled-feature gradient
-        g_feat = self.tlod.functional.grl_backward(feat.grad, 0.1)
-        results[dom] = (rois, feat.grad, g_feat, torch.stack([img, ins, cst]).detach(), score.grad, prob.grad)
-        feat.grad = None
+        img, ins, cst = self.tlod.da_losses(score, prob, dl)
+        (0.1 * (img + ins + cst)).backward()
+        out = (torch.stack([img, ins, cst]).detach(), score.grad, prob.grad)
         score.grad = None
         prob.grad = None
+        return out
 
-    def device_part(self, d, copy_in=None, copy_out=None):
-        """Source and target domain are independent until the losses are summed: each runs on its
-        own stream (one CUDA graph per domain when captured), so the latency-bound kernels of one
-        domain can fill SMs the other leaves idle.  copy_in / copy_out (e2e mode) put each
-        domain's H2D / D2H copies on the same stream, overlapping the other domain's compute."""
-        results = {}
-        cur = torch.cuda.current_stream(self.dev)
-        if self.streams is None:
-            self.streams = {"src": torch.cuda.Stream(self.dev), "tgt": torch.cuda.Stream(self.dev)}
-        for dom in ("src", "tgt"):
-            st = self.streams[dom]
-            st.wait_stream(cur)
-            with torch.cuda.stream(st):
-                if copy_in is not None:
-                    copy_in(dom)
-                if self.graphs is not None and d is self.d:
-                    self.graphs[dom].replay()
-                    results[dom] = self.static[dom]
-                else:
-                    self.domain(dom, d, results)
-                if copy_out is not None:
-                    copy_out(dom, results)
-        for dom in ("src", "tgt"):
-            cur.wait_stream(self.streams[dom])
-        return results
+    def pool_part(self, dom, d, rois_flat):
+        feat = d[dom + "_feat"].requires_grad_(True)
+        pooled = self.roi_align(feat, rois_flat)
+        pooled.backward(self.top[dom])
+        g_feat = self.tlod.functional.grl_backward(feat.grad, 0.1)  # GRL in front of the image DA head
+        out = (feat.grad, g_feat)
+        feat.grad = None
+        return out
 
-    def anchor_part(self, d, results):
-        results["anchor_targets"] = self.anchor_target((d["src_prob"], d["src_gt"], d["src_im_info"],
-                                                        self.num_boxes))
-        return results
+    def src1(self, d):
+        rois = self.proposal((d["src_prob"], d["src_deltas"], d["src_im_info"], "TRAIN"))
+        return rois, self.proposal_target.begin(rois, d["src_gt"], self.num_boxes, host=self.pt_host)
+
+    def src2(self, d, pt_state, keep, fg):
+        rois, labels, targets, inside, outside = self.proposal_target.finish(pt_state, keep, fg)
+        return {"rois": rois, "labels": labels, "targets": targets, "pool": self.pool_part("src", d, rois.view(-1, 5))}
+
+    def src3(self, d, at):
+        """Source-domain work that does not wait for the sampled RoIs: DA losses, RPN losses."""
+        da = self.da_part("src", d, None)
+        cls = d["src_rpn_cls"].requires_grad_(True)
+        box = d["src_rpn_box"].requires_grad_(True)
+        l_cls, l_box = self.tlod.rpn_losses(cls, box, at[0], at[1], at[2], at[3])
+        (l_cls + l_box).backward()
+        out = {"da": da, "rpn": (torch.stack([l_cls, l_box]).detach(), cls.grad, box.grad)}
+        cls.grad = None
+        box.grad = None
+        return out
+
+    def tgt(self, d):
+        rois = self.proposal((d["tgt_prob"], d["tgt_deltas"], d["tgt_im_info"], "TEST"))
+        flat = rois.reshape(-1, 5)
+        return {"rois": rois, "pool": self.pool_part("tgt", d, flat), "da": self.da_part("tgt", d, rois)}
 
     def capture(self):
-        """Warm up on a side stream, then capture one CUDA graph per domain over the static inputs."""
+        """Warm up eagerly (allocator, lazy module state), then capture the three graphs."""
         try:
             side = torch.cuda.Stream(self.dev)
             side.wait_stream(torch.cuda.current_stream(self.dev))
             with torch.cuda.stream(side):
                 for _ in range(3):
-                    r = {}
-                    self.domain("src", self.d, r)
-                    self.domain("tgt", self.d, r)
+                    self.step_eager()
             torch.cuda.current_stream(self.dev).wait_stream(side)
             torch.cuda.synchronize(self.dev)
-            graphs, static = {}, {}
+            at = self.anchor_target((self.d["src_prob"], self.d["src_gt"], self.d["src_im_info"], self.num_boxes))
+            self.at_static = [t.clone() for t in at]
+            n_inside = self.anchor_target._inside(H, W, 1200, 600, self.dev)[0].size(0)
+            self.at_host = torch.empty((self.wl.n_src, n_inside), dtype=torch.float32).pin_memory()
+            graphs = {}
             n0 = self.tlod.launch_count()
-            for dom in ("src", "tgt"):
-                graphs[dom] = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graphs[dom]):
-                    self.domain(dom, self.d, static)
+            graphs["at1"] = torch.cuda.CUDAGraph()   # anchor labels + their pinned D2H copy
+            with torch.cuda.graph(graphs["at1"]):
+                self.static["at1"] = self.anchor_target.launch_labels(self.d["src_gt"], H, W, (600, 1200),
+                                                                      labels_host=self.at_host)
+            graphs["src1"] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graphs["src1"]):
+                self.static["src1"] = self.src1(self.d)
+            graphs["src2"] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graphs["src2"]):
+                self.static["src2"] = self.src2(self.d, self.static["src1"][1], self.keep_d, self.fg_d)
+            graphs["src3"] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graphs["src3"]):
+                self.static["src3"] = self.src3(self.d, self.at_static)
+            graphs["tgt"] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graphs["tgt"]):
+                self.static["tgt"] = self.tgt(self.d)
             self.launches_per_replay = int(self.tlod.launch_count() - n0)
-            for dom in ("src", "tgt"):
-                graphs[dom].replay()
             torch.cuda.synchronize(self.dev)
-            self.graphs, self.static = graphs, static
-            self.graph = graphs
+            self.graphs = graphs
         except Exception as e:  # noqa: BLE001 -- eager is always available
-            sys.stderr.write("bench.py: CUDA graph capture failed (%s); running eagerly\n" % (e,))
-            self.graph = self.graphs = self.static = None
+            sys.stderr.write("bench.py: CUDA graph capture failed (%r); running eagerly\n" % (e,))
+            self.graphs = None
 
-    def step(self, d=None, copy_in=None, copy_out=None):
-        d = self.d if d is None else d
-        # Queue the two domains first (two graph launches), then start the anchor-target layer on a
-        # side stream that only depends on the step's inputs: its label kernels run beside the
-        # domain graphs, and its host-side subsampling (numpy's RNG stream, like the reference)
-        # runs while the GPU works through the queue.
+    def step_eager(self):
+        d = self.d
+        res = {}
+        res["tgt"] = self.tgt(d)
+        pending = self.anchor_target.begin((d["src_prob"], d["src_gt"], d["src_im_info"], self.num_boxes),
+                                           im_hw=(600, 1200))
+        rois, st = self.src1(d)
+        # numpy RNG order of the reference step: anchor-target layer (inside the RPN), then proposal targets
+        at = self.anchor_target.finish(pending)
+        keep, fg = self.proposal_target.sample(st)
+        res["src"] = dict(self.src2(d, st, keep, fg), **self.src3(d, at))
+        res["anchor_targets"] = at
+        return res
+
+    def step(self, copy_in=None):
+        """copy_in (e2e mode) puts each domain's H2D copy on that domain's stream."""
+        if self.graphs is None:
+            if copy_in is not None:
+                copy_in("src"), copy_in("tgt")
+            return self.step_eager()
+        d = self.d
         cur = torch.cuda.current_stream(self.dev)
-        if self.side is None:
-            self.side = torch.cuda.Stream(self.dev)
-        self.side.wait_stream(cur)
-        results = self.device_part(d, copy_in, copy_out)
-        with torch.cuda.stream(self.side):
-            pending = self.anchor_target.begin((d["src_prob"], d["src_gt"], d["src_im_info"], self.num_boxes))
-        results["anchor_targets"] = self.anchor_target.finish(pending)
-        return results
+        s_src, s_tgt, s_side = self.streams["src"], self.streams["tgt"], self.streams["side"]
+        for s in (s_src, s_tgt, s_side):
+            s.wait_stream(cur)
+        with torch.cuda.stream(s_src):
+            if copy_in is not None:
+                copy_in("src")
+                arrived = torch.cuda.Event()
+                arrived.record(s_src)
+                s_side.wait_event(arrived)  # the anchor-target layer reads inputs this copy delivers
+        # the anchor-target layer goes first: its label kernels + pinned D2H head the host chain
+        with torch.cuda.stream(s_side):
+            self.graphs["at1"].replay()
+            pending = self.static["at1"]
+            pending["copied"] = torch.cuda.Event()
+            pending["copied"].record(s_side)
+            pending["stream"] = s_side
+        with torch.cuda.stream(s_src):
+            self.graphs["src1"].replay()
+            copied = torch.cuda.Event()
+            copied.record(s_src)
+        with torch.cuda.stream(s_tgt):
+            if copy_in is not None:
+                copy_in("tgt")
+            self.graphs["tgt"].replay()
+        # host, in the reference's RNG order: anchor subsampling (inside the RPN), then the fg / bg sampling
+        with torch.cuda.stream(s_side):
+            at = self.anchor_target.finish(pending)
+            for dst, src in zip(self.at_static, at):
+                dst.copy_(src, non_blocking=True)
+            self.graphs["src3"].replay()
+        st = self.static["src1"][1]
+        st["copied"] = copied
+        keep, fg = self.proposal_target.sample(st)
+        self.keep_h.numpy()[...] = keep
+        self.fg_h.numpy()[...] = fg
+        with torch.cuda.stream(s_src):
+            self.keep_d.copy_(self.keep_h, non_blocking=True)
+            self.fg_d.copy_(self.fg_h, non_blocking=True)
+            self.graphs["src2"].replay()
+        for s in (s_src, s_tgt, s_side):
+            cur.wait_stream(s)
+        return {"src": dict(self.static["src2"], **self.static["src3"]), "tgt": self.static["tgt"],
+                "anchor_targets": self.at_static}
+
+    # ---- end to end through host buffers ----
+    def e2e_outputs(self, r):
+        out = {"src_rois": r["src"]["rois"], "src_labels": r["src"]["labels"], "src_targets": r["src"]["targets"],
+               "src_gfeat": r["src"]["pool"][1], "src_losses": r["src"]["da"][0], "src_rpn_losses": r["src"]["rpn"][0],
+               "tgt_rois": r["tgt"]["rois"], "tgt_gfeat": r["tgt"]["pool"][1], "tgt_losses": r["tgt"]["da"][0],
+               "anchor_labels": r["anchor_targets"][0]}
+        return out
 
     def step_e2e(self):
-        """Same step through host buffers: H2D of the inputs from pinned memory into the static
-        device buffers, the step, D2H of the results into pinned host buffers; each domain's
-        copies ride on that domain's stream."""
-        d = self.d
-
-        def copy_in(dom):
-            for k, v in self.host.items():
-                if k.startswith(dom) and k not in ("src_gt", "src_im_info"):
-                    d[k].detach().copy_(v, non_blocking=True)
-
-        def copy_out(dom, results):
-            rois, gfeat, _, losses, _, _ = results[dom]
-            outs = [rois, gfeat, losses]
-            if self.host_out is None:
-                self.host_out = {}
-            if dom not in self.host_out:
-                self.host_out[dom] = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
-            for h, o in zip(self.host_out[dom], outs):
-                h.copy_(o, non_blocking=True)
-
-        d["src_gt"].copy_(self.host["src_gt"], non_blocking=True)  # the anchor-target layer reads these
-        d["src_im_info"].copy_(self.host["src_im_info"], non_blocking=True)
-        d["src_prob"].detach().copy_(self.host["src_prob"], non_blocking=True)
-        r = self.step(None, copy_in, copy_out)
-        at = r["anchor_targets"]
-        if "at" not in self.host_out:
-            self.host_out["at"] = torch.empty(at[0].shape, dtype=at[0].dtype).pin_memory()
-        self.host_out["at"].copy_(at[0], non_blocking=True)
+        """Same step through host buffers: each domain's inputs arrive with one H2D copy from a pinned
+        arena on that domain's stream; the results leave packed in one pinned arena with one D2H copy."""
+        r = self.step(copy_in=lambda dom: self.arena[dom].h2d())
+        outs = self.e2e_outputs(r)
+        if self.out_arena is None:
+            self.out_arena = Arena(outs, self.dev, False)
+        for k, v in outs.items():
+            self.out_arena.dviews[k].copy_(v.reshape(self.out_arena.dviews[k].shape), non_blocking=True)
+        self.out_arena.d2h()
         torch.cuda.current_stream(self.dev).synchronize()
-        return self.host_out
+        return self.out_arena.hviews
 
     def e2e_bytes(self):
-        h2d = sum(v.numel() * v.element_size() for v in self.host.values())
-        d2h = 0
-        for dom, n, per in (("src", N_SRC, 2000), ("tgt", N_TGT, 300)):
-            d2h += n * per * 5 * 4 + n * C * H * W * 4 + 3 * 4
-        d2h += N_SRC * A * H * W * 4
+        h2d = sum(a.nbytes for a in self.arena.values())
+        d2h = self.out_arena.nbytes if self.out_arena is not None else 0
         return h2d, d2h
+
+    def check_graph_against_eager(self):
+        """The captured graphs must produce what the eager modules produce (same numpy RNG state)."""
+        if self.graphs is None:
+            return "eager (no graphs)"
+        state = np.random.get_state()
+        a = self.step()
+        torch.cuda.synchronize(self.dev)
+        keys = ("src_rois", "src_labels", "src_targets", "src_gfeat", "src_losses", "src_rpn_losses", "tgt_rois",
+                "tgt_gfeat", "tgt_losses", "anchor_labels")
+        got = {k: v.clone() for k, v in self.e2e_outputs(a).items()}
+        np.random.set_state(state)
+        b = self.e2e_outputs(self.step_eager())
+        torch.cuda.synchronize(self.dev)
+        for k in keys:
+            x, y = got[k], b[k].reshape(got[k].shape)
+            if not torch.allclose(x, y, rtol=1e-5, atol=1e-7, equal_nan=True):
+                raise SystemExit("bench.py: CUDA-graph replay differs from the eager step in %s (max |d| = %g)"
+                                 % (k, float((x - y).abs().max())))
+        return "graph replay == eager step on %d outputs" % len(keys)
 
 
 def clocks_sampler(path):
@@ -271,81 +426,93 @@ def parse_clocks(path):
     return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons)}
 
 
-def roi_align_cfg3(dev, iters=20):
-    """RoIAlign 8x8 forward and backward at BASELINE cfg3 (ResNet-101 conv4, batch 8, 256 RoIs/image):
-    630 MB of algorithmic traffic per direction, larger than L2, so no flush is needed."""
+def per_call_us(fn, iters=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters * 1e3
+
+
+def load_traffic(section):
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            return json.load(f).get(section, {})
+    except Exception:  # noqa: BLE001
+        return {}
+
+
+def roi_align_sizes(dev):
+    """RoIAlign(8, 8) and RoIAlignAvg(7, 7) forward / backward alone at the BASELINE shapes: cfg1 and cfg2
+    (L2 resident), cfg3 (630 MB of algorithmic traffic per direction: larger than L2, no flush needed)."""
     from tools.synth import synth_rois
     from tlod_b200 import functional as F
     peak, peak_src = peaks()
-    B, Cc, Hh, Ww, R = 8, 1024, 38, 75, 2048
+    out = {"peak_GBps": peak, "peak_source": peak_src}
     g = torch.Generator().manual_seed(7)
-    x = torch.relu(torch.randn(B, Cc, Hh, Ww, generator=g)).to(dev)
-    rois = synth_rois(R, B, 41).to(dev)
-    rois = rois[torch.argsort(rois[:, 0], stable=True)].contiguous()  # (B, 256, 5).view(-1, 5) order
-    top = torch.randn(R, Cc, 8, 8, device=dev)
-    alg = B * Cc * Hh * Ww * 4 + R * 20 + R * Cc * 64 * 4
-    plan = F.roi_align_plan(rois, x.shape, 8, 8, 1.0 / 16)
-    traffic = {}
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            traffic = json.load(f).get("cfg3", {})
-    except Exception:  # noqa: BLE001
-        pass
-    out = {}
-    for name, kern, fn in (("plan", None, lambda: F.roi_align_plan(rois, x.shape, 8, 8, 1.0 / 16)),
-                           ("fwd", "roi_align_fwd_planes_kernel",
-                            lambda: F.roi_align_forward(x, rois, 8, 8, 1.0 / 16, plan=plan)),
-                           ("bwd", "roi_align_bwd_rows_kernel",
-                            lambda: F.roi_align_backward(top, rois, x.shape, 1.0 / 16, plan=plan))):
-        for _ in range(3):
-            fn()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(iters):
-            fn()
-        b.record()
-        torch.cuda.synchronize()
-        ms = a.elapsed_time(b) / iters
-        if kern is None:
-            out[name] = {"ms": ms}
-        else:
-            out[name] = {"ms": ms, "achieved_GBps": alg / ms / 1e6, "frac_of_hbm_peak": alg / ms / 1e6 / peak,
-                         "traffic": traffic.get(kern)}
-    out["algorithmic_bytes_per_direction"] = alg
-    total_ms = out["plan"]["ms"] + out["fwd"]["ms"] + out["bwd"]["ms"]
-    out["rois_per_s_fwd_bwd"] = R / (total_ms * 1e-3)
-    out["frac_fwd_bwd"] = 2 * alg / (total_ms * 1e6) / peak
-    out["peak_GBps"] = peak
-    out["peak_source"] = peak_src
+    for name, (B, Cc, Hh, Ww, R) in (("cfg1", (1, 512, 37, 75, 128)), ("cfg2", (2, 512, 37, 75, 512)),
+                                     ("cfg3", (8, 1024, 38, 75, 2048))):
+        x = torch.relu(torch.randn(B, Cc, Hh, Ww, generator=g)).to(dev)
+        rois = synth_rois(R, B, 41)
+        rois = rois[torch.argsort(rois[:, 0], stable=True)].contiguous().to(dev)  # (B, R/B, 5).view(-1, 5) order
+        top8 = torch.randn(R, Cc, 8, 8, device=dev)
+        top7 = torch.randn(R, Cc, 7, 7, device=dev)
+        feat_b = B * Cc * Hh * Ww * 4 + R * 20
+        alg8, alg7 = feat_b + R * Cc * 64 * 4, feat_b + R * Cc * 49 * 4
+        plan = F.roi_align_plan(rois, x.shape, 8, 8, 1.0 / 16)
+        it = 20
+        t = {"plan": per_call_us(lambda: F.roi_align_plan(rois, x.shape, 8, 8, 1.0 / 16), it),
+             "fwd": per_call_us(lambda: F.roi_align_forward(x, rois, 8, 8, 1.0 / 16, plan=plan), it),
+             "bwd": per_call_us(lambda: F.roi_align_backward(top8, rois, x.shape, 1.0 / 16, plan=plan), it),
+             "avg_fwd": per_call_us(lambda: F.roi_align_avg_forward(x, rois, 7, 7, 1.0 / 16, plan=plan), it),
+             "avg_bwd": per_call_us(lambda: F.roi_align_avg_backward(top7, rois, x.shape, 1.0 / 16, plan=plan), it)}
+
+        def frac(nbytes, us):
+            return nbytes / (us * 1e-6) / 1e9 / peak
+        traffic = load_traffic(name)
+        e = {"shape": [B, Cc, Hh, Ww, R], "l2_resident": name != "cfg3", "plan": {"us": t["plan"]},
+             "fwd": {"us": t["fwd"], "kernel": "roi_align_fwd8_kernel", "algorithmic_bytes": alg8,
+                     "achieved_GBps": alg8 / t["fwd"] / 1e3, "frac_of_hbm_peak": frac(alg8, t["fwd"]),
+                     "traffic": traffic.get("roi_align_fwd8_kernel")},
+             "bwd": {"us": t["bwd"], "kernel": "roi_align_bwd_rows_kernel", "algorithmic_bytes": alg8,
+                     "achieved_GBps": alg8 / t["bwd"] / 1e3, "frac_of_hbm_peak": frac(alg8, t["bwd"]),
+                     "traffic": traffic.get("roi_align_bwd_rows_kernel")},
+             "avg_fwd": {"us": t["avg_fwd"], "kernel": "roi_align_avg_fwd8_kernel (fused 2x2 average)",
+                         "algorithmic_bytes_fused": alg7, "frac_of_hbm_peak_fused_bytes": frac(alg7, t["avg_fwd"]),
+                         "frac_of_hbm_peak_op_surface_bytes": frac(alg8 + R * Cc * (64 + 49) * 4, t["avg_fwd"]),
+                         "traffic": traffic.get("roi_align_avg_fwd8_kernel")},
+             "avg_bwd": {"us": t["avg_bwd"], "kernel": "avgpool2x2_bwd_kernel + roi_align_bwd_rows_kernel",
+                         "algorithmic_bytes_fused": alg7, "frac_of_hbm_peak_fused_bytes": frac(alg7, t["avg_bwd"]),
+                         "frac_of_hbm_peak_op_surface_bytes": frac(alg8 + R * Cc * (64 + 49) * 4, t["avg_bwd"])},
+             "rois_per_s_fwd_bwd": R / ((t["plan"] + t["fwd"] + t["bwd"]) * 1e-6),
+             "frac_fwd_bwd": frac(2 * alg8, t["plan"] + t["fwd"] + t["bwd"]),
+             "rois_per_s_avg_fwd_bwd": R / ((t["plan"] + t["avg_fwd"] + t["avg_bwd"]) * 1e-6),
+             "frac_avg_fwd_bwd_fused_bytes": frac(2 * alg7, t["plan"] + t["avg_fwd"] + t["avg_bwd"])}
+        out[name] = e
+        del x, top8, top7
     out["note"] = ("back-to-back launches, CUDA events around the loop; each call includes its torch.empty "
-                   "(caching allocator); the plan is built once per rois tensor and shared by fwd and bwd")
+                   "(caching allocator); the plan is built once per rois tensor and shared by fwd and bwd; "
+                   "'op surface' bytes count the (R,C,8,8) tensor written and re-read by the unfused reference path")
     return out
 
 
 def secondary_metrics(dev, iters=20):
     """The other metrics SURVEY 8(d) names, measured alone on rank 0: the two proposal pipelines
-    (12000 -> 2000 TRAIN, 6000 -> 300 TEST; proposal sets/s, proposals/s, fraction of the bound
-    8(d) defines: max(bytes / HBM rate, 16 flop per upper-triangle pair / fp32 SIMT rate)), the
-    cfg5 NMS sweep (batch x IoU threshold) and RoIPool forward + backward."""
+    (fraction of the bound 8(d) defines: max(bytes / HBM rate, 16 flop per upper-triangle pair / fp32
+    SIMT rate)), the cfg5 NMS sweep, plain NMS, RoIPool, RoICrop (unfused and fused with its max-pool)
+    and the multi-level DA losses at cfg4 map sizes."""
     from tools.synth import synth_rois, synth_rpn
     from model.rpn.generate_anchors import generate_anchors
+    from model.utils.net_utils import _affine_grid_gen
     from tlod_b200 import functional as F
+    import tlod_b200
     peak, _ = peaks()
     fp32_tflops = 148 * 128 * 2 * 1.965e9 / 1e12  # nominal SIMT rate (SURVEY 8d)
-
-    def per_call_us(fn):
-        for _ in range(3):
-            fn()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(iters):
-            fn()
-        b.record()
-        torch.cuda.synchronize()
-        return a.elapsed_time(b) / iters * 1e3
-
     anchors = torch.from_numpy(generate_anchors(scales=np.array([4, 8, 16, 32]),
                                                 ratios=np.array([0.5, 1, 2]))).float().to(dev)
     out = {"fp32_simt_tflops_nominal": fp32_tflops, "proposal_layer": {}, "nms_sweep_test_6000_300": []}
@@ -360,53 +527,137 @@ def secondary_metrics(dev, iters=20):
 
     for name, pre, post in (("TRAIN_12000_2000", 12000, 2000), ("TEST_6000_300", 6000, 300)):
         prob, deltas, info = rpn(2)
-        us = per_call_us(lambda: F.proposals(prob, deltas, info, anchors, 16, pre, post, 0.7))
+        rois, order, boxes, num = F.proposals(prob, deltas, info, anchors, 16, pre, post, 0.7, return_debug=True)
+        us = per_call_us(lambda: F.proposals(prob, deltas, info, anchors, 16, pre, post, 0.7), iters)
         nbytes = 2 * (A * H * W * 4 * 5 + post * 20)
         flops = 2 * (pre * (pre - 1) / 2) * 16
         bound_us = max(nbytes / (peak * 1e9), flops / (fp32_tflops * 1e12)) * 1e6
         out["proposal_layer"][name] = {"images": 2, "us_per_call": us, "proposal_sets_per_s": 2 / (us * 1e-6),
                                        "proposals_per_s": 2 * post / (us * 1e-6), "bound_us": bound_us,
-                                       "frac_of_bound": bound_us / us,
+                                       "frac_of_bound": bound_us / us, "kept": [int(v) for v in num.tolist()],
                                        "note": "bound = full upper-triangle IoU work on the nominal fp32 SIMT "
                                                "rate; the phased NMS computes only the triangle the scan reaches"}
     for batch in (1, 8, 64):
         prob, deltas, info = rpn(batch)
         for thr in (0.3, 0.5, 0.7):
-            us = per_call_us(lambda: F.proposals(prob, deltas, info, anchors, 16, 6000, 300, thr))
+            us = per_call_us(lambda: F.proposals(prob, deltas, info, anchors, 16, 6000, 300, thr), iters)
             out["nms_sweep_test_6000_300"].append({"batch": batch, "iou": thr, "us_per_call": us,
                                                    "proposal_sets_per_s": batch / (us * 1e-6)})
-    # RoIPool 7x7 forward + backward at cfg1 / cfg2 scale (VGG16 conv5, 2 images, 512 RoIs)
+    # plain NMS on score-sorted boxes (the reference's nms_cuda_compute workload)
+    from tools.reference_bench import sorted_boxes
+    for n in (12000, 6000):
+        dets = sorted_boxes(n, 500 + n).to(dev)
+        out["nms_%d" % n] = {"us": per_call_us(lambda: F.nms_device(dets, 0.7), iters), "thresh": 0.7,
+                             "note": "device-resident keep + count, no host synchronisation"}
+    # RoIPool 7x7 forward + backward at cfg2 scale (VGG16 conv5, 2 images, 512 RoIs)
     g = torch.Generator().manual_seed(5)
     feat = torch.relu(torch.randn(2, C, H, W, generator=g)).to(dev)
-    rois = synth_rois(512, 2, 41).to(dev)
+    rois = synth_rois(512, 2, 41)
+    rois = rois[torch.argsort(rois[:, 0], stable=True)].contiguous().to(dev)
     top = torch.randn(512, C, 7, 7, device=dev)
     pooled, argmax = F.roi_pool_forward(feat, rois, 7, 7, 1.0 / 16)
-    us_f = per_call_us(lambda: F.roi_pool_forward(feat, rois, 7, 7, 1.0 / 16))
-    us_b = per_call_us(lambda: F.roi_pool_backward(top, argmax, rois, feat.shape, 1.0 / 16))
+    us_f = per_call_us(lambda: F.roi_pool_forward(feat, rois, 7, 7, 1.0 / 16), iters)
+    us_b = per_call_us(lambda: F.roi_pool_backward(top, argmax, rois, feat.shape, 1.0 / 16), iters)
     alg_f = feat.numel() * 4 + 512 * 20 + 512 * C * 49 * 8
-    out["roi_pool_2x512x37x75_512rois"] = {
+    out["roi_pool_cfg2"] = {
         "fwd_us": us_f, "bwd_us": us_b, "rois_per_s_fwd_bwd": 512 / ((us_f + us_b) * 1e-6),
         "frac_of_hbm_peak_fwd": alg_f / (us_f * 1e-6) / 1e9 / peak,
         "frac_of_hbm_peak_bwd": alg_f / (us_b * 1e-6) / 1e9 / peak,
-        "note": "L2-warm back-to-back launches (working set 63 MB < L2)"}
-    # BASELINE cfg3 (ii): the crop path -- RoICrop 14x14 on conv4 (8, 1024, 38, 75), 2048 RoIs
-    from model.utils.net_utils import _affine_grid_gen
+        "note": "L2-warm back-to-back launches (working set 63 MB < L2); bound by the instruction count of the "
+                "strict-> window scan (~10 cell visits per output), see profiles/r02_rejected_roi_pool_planes_ncu.txt"}
+    # BASELINE cfg3 (ii): the crop path -- RoICrop 14x14 on conv4 (8, 1024, 38, 75), 2048 RoIs, then max-pool 7x7
     Bc, Cc, Hc, Wc, Rc, G = 8, 1024, 38, 75, 2048, 14
     featc = torch.relu(torch.randn(Bc, Cc, Hc, Wc, generator=g)).to(dev)
     roisc = synth_rois(Rc, Bc, 41)
     roisc = roisc[torch.argsort(roisc[:, 0], stable=True)].contiguous().to(dev)
     grid_xy = _affine_grid_gen(roisc, (Hc, Wc), G)
     grid_yx = torch.stack([grid_xy[..., 1], grid_xy[..., 0]], 3).contiguous()
+    gy, gx = grid_xy[:, :, 0, 1].contiguous(), grid_xy[:, 0, :, 0].contiguous()
     topc = torch.randn(Rc, Cc, G, G, device=dev)
-    us_cf = per_call_us(lambda: F.roi_crop_forward(featc, grid_yx))
-    us_cb = per_call_us(lambda: F.roi_crop_backward(topc, grid_yx, featc.shape))
+    top7 = torch.randn(Rc, Cc, 7, 7, device=dev)
+    us_cf = per_call_us(lambda: F.roi_crop_forward(featc, grid_yx), 5, 2)
+    us_cb = per_call_us(lambda: F.roi_crop_backward(topc, grid_yx, featc.shape), 5, 2)
+    o7, a7 = F.roi_crop_pool_forward(featc, gy, gx)
+    us_pf = per_call_us(lambda: F.roi_crop_pool_forward(featc, gy, gx), 5, 2)
+    us_pb = per_call_us(lambda: F.roi_crop_pool_backward(top7, a7, gy, gx, featc.shape), 5, 2)
     alg_c = featc.numel() * 4 + grid_yx.numel() * 4 + Rc * Cc * G * G * 4
+    alg_p = featc.numel() * 4 + Rc * 28 * 4 + Rc * Cc * 49 * 5
     out["roi_crop_cfg3_14x14"] = {
-        "fwd_us": us_cf, "bwd_us": us_cb, "rois_per_s_fwd_bwd": Rc / ((us_cf + us_cb) * 1e-6),
-        "algorithmic_bytes_per_direction": alg_c,
+        "fwd_us": us_cf, "bwd_us": us_cb, "algorithmic_bytes_per_direction": alg_c,
         "frac_of_hbm_peak_fwd": alg_c / (us_cf * 1e-6) / 1e9 / peak,
-        "frac_of_hbm_peak_bwd": alg_c / (us_cb * 1e-6) / 1e9 / peak}
+        "frac_of_hbm_peak_bwd": alg_c / (us_cb * 1e-6) / 1e9 / peak,
+        "fused_with_max_pool": {
+            "fwd_us": us_pf, "bwd_us": us_pb, "algorithmic_bytes_fused": alg_p,
+            "frac_of_hbm_peak_fwd_fused_bytes": alg_p / (us_pf * 1e-6) / 1e9 / peak,
+            "frac_of_hbm_peak_bwd_fused_bytes": alg_p / (us_pb * 1e-6) / 1e9 / peak,
+            "frac_of_hbm_peak_fwd_op_surface_bytes": alg_c / (us_pf * 1e-6) / 1e9 / peak,
+            "frac_of_hbm_peak_bwd_op_surface_bytes": alg_c / (us_pb * 1e-6) / 1e9 / peak,
+            "rois_per_s_fwd_bwd": Rc / ((us_pf + us_pb) * 1e-6),
+            "note": "crop 14x14 -> max_pool2d(2,2) as one kernel each way: the 1.64 GB sample tensor is never written"}}
+    del featc, topc, top7, o7, a7
+    # multi-level image DA losses at cfg4 map sizes (8 images): conv3 / conv4 / conv5 + instance CE
+    maps = [torch.randn(8, 2, 150, 300, device=dev), torch.randn(8, 2, 75, 150, device=dev),
+            torch.randn(8, 2, 37, 75, device=dev), torch.randn(2048, 2, 1, 1, device=dev)]
+    lo = F.da_image_loss_forward(maps, 1)
+    out["da_image_losses_cfg4"] = {
+        "fwd_us": per_call_us(lambda: F.da_image_loss_forward(maps, 1), iters),
+        "bwd_us": per_call_us(lambda: F.da_image_loss_backward(maps, 1, lo), iters),
+        "levels": [list(m.shape) for m in maps], "launches": "1 forward (+ an 80-byte memset), 1 backward"}
     return out
+
+
+def reference_subprocess(cpu_steps, timeout=900):
+    """tools/reference_bench.py in its own process: the reference's recompiled CUDA kernels, its CPU
+    RoIAlign as shipped and the oracle port -- nothing under oracle/ is mapped into this process."""
+    try:
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "reference_bench.py"), "--cpu-steps",
+                            str(cpu_steps)], capture_output=True, text=True, timeout=timeout)
+        lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+        if p.returncode != 0 or not lines:
+            return {"error": "reference_bench.py rc=%d: %s" % (p.returncode, p.stderr[-400:])}
+        return json.loads(lines[-1])
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)}
+
+
+def speedups(ref, mine_align, secondary):
+    """Same-box GPU-vs-GPU ratios: reference kernel time / this library's time."""
+    out = {}
+    g = ref.get("gpu_reference", {}) if isinstance(ref, dict) else {}
+    for cfg_name in ("cfg1", "cfg2", "cfg3"):
+        r, m = g.get("roi_align_" + cfg_name), mine_align.get(cfg_name) if mine_align else None
+        if r and m:
+            out["roi_align_%s_fwd" % cfg_name] = r["fwd_us"] / m["fwd"]["us"]
+            out["roi_align_%s_bwd" % cfg_name] = r["bwd_us"] / m["bwd"]["us"]
+    if secondary:
+        r = g.get("roi_pool_cfg2")
+        if r:
+            out["roi_pool_cfg2_fwd"] = r["fwd_us"] / secondary["roi_pool_cfg2"]["fwd_us"]
+            out["roi_pool_cfg2_bwd"] = r["bwd_us"] / secondary["roi_pool_cfg2"]["bwd_us"]
+        r = g.get("roi_crop_cfg3")
+        if r:
+            c = secondary["roi_crop_cfg3_14x14"]
+            out["roi_crop_cfg3_fwd"] = r["fwd_us"] / c["fwd_us"]
+            out["roi_crop_cfg3_bwd"] = r["bwd_us"] / c["bwd_us"]
+        for n in (12000, 6000):
+            r = g.get("nms_%d" % n)
+            if r:
+                out["nms_%d" % n] = r["us"] / secondary["nms_%d" % n]["us"]
+    return out
+
+
+def bind_rank_to_cores(local, world_local):
+    """Give every rank its own slice of the host cores before any pinned allocation (first touch
+    then places the pinned pages near those cores)."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = max(len(cores) // max(world_local, 1), 1)
+        mine = cores[local * per:(local + 1) * per] or cores
+        os.sched_setaffinity(0, mine)
+        torch.set_num_threads(max(1, min(len(mine), 4)))
+        return len(mine)
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def run_tlod(args):
@@ -417,6 +668,7 @@ def run_tlod(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
                          "(use --impl reference for the CPU arm)")
+    cores_bound = bind_rank_to_cores(local, int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))) if world > 1 else None
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -425,7 +677,10 @@ def run_tlod(args):
     import tlod_b200
     from tlod_b200 import _lib
 
-    step = TlodStep(dev, seed=3 + rank, use_graph=not args.no_graph)
+    wl = Workload(args.workload)
+    step = TlodStep(dev, seed=3 + rank, wl=wl, use_graph=not args.no_graph)
+    used_graph = step.graphs is not None
+    graph_check = step.check_graph_against_eager()
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
 
     def barrier():
@@ -448,27 +703,29 @@ def run_tlod(args):
             evs.append((a, b))
         barrier()
         wall = time.perf_counter() - wall0
-        ms = sum(a.elapsed_time(b) for a, b in evs)
+        ms_own = sum(a.elapsed_time(b) for a, b in evs)
+        ranks = [ms_own]
         if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, wall
+            t = torch.tensor([ms_own], device=dev, dtype=torch.float64)
+            allv = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allv, t)
+            ranks = [float(v.item()) for v in allv]
+        return max(ranks), wall, ranks
 
     clock_file = os.path.join(ROOT, "gpurun_out", "bench_clocks_rank0.csv")
     os.makedirs(os.path.dirname(clock_file), exist_ok=True)
     sampler = clocks_sampler(clock_file) if rank == 0 else None
     launches0 = tlod_b200.launch_count()
-    ms_dev, wall = timed(step.step, args.steps, args.warmup)
+    ms_dev, wall, ranks_dev = timed(step.step, args.steps, args.warmup)
     # kernels of this library inside the timed region: eager launches are counted by the library;
     # a graph replay re-issues the launches counted once at capture time
     eager_per_step = (tlod_b200.launch_count() - launches0) // (args.steps + args.warmup)
-    launches = (eager_per_step + (step.launches_per_replay if step.graph is not None else 0)) * args.steps
-    ms_e2e, _ = timed(step.step_e2e, args.steps, max(3, args.warmup // 2))
+    launches = (eager_per_step + (step.launches_per_replay if used_graph else 0)) * args.steps
+    ms_e2e, _, ranks_e2e = timed(step.step_e2e, args.steps, max(3, args.warmup // 2))
 
-    # cfg4 companion number (N > 1 only): the same step while the training loop's data-parallel
-    # gradient all-reduce (a VGG16-DAF sized fp32 buffer, ~570 MB, NCCL over NVLink) is in flight.
-    # It is NOT part of the path (no data-path collective); reported beside `value`, never inside it.
+    # BASELINE config 4 companion: the same step while the training loop's data-parallel gradient all-reduce
+    # (a VGG16-DAF sized fp32 buffer, ~570 MB, NCCL over NVLink) is in flight.  It is NOT part of the
+    # path (no data-path collective); reported beside `value`, never inside it.
     ms_ar = None
     if world > 1:
         grads = torch.zeros(142 * 1000 * 1000, dtype=torch.float32, device=dev)
@@ -477,30 +734,52 @@ def run_tlod(args):
             work = dist.all_reduce(grads, async_op=True)
             step.step()
             work.wait()
-        ms_ar, _ = timed(step_with_allreduce, args.steps, 3)
+        ms_ar, _, _ = timed(step_with_allreduce, args.steps, 3)
         del grads
     if sampler is not None:
         sampler.terminate()
         sampler.wait()
 
-    # per-kernel device time (CUDA events on the launch stream, inside the library)
+    # per-kernel device time (CUDA events on the launch stream, inside the library), eager step
     _lib.profile_reset()
     _lib.profile(True)
-    graphs, step.graphs = step.graphs, None  # eager: the library brackets each launch with events
     for _ in range(max(5, min(args.steps, 20))):
         flush.zero_()
-        step.anchor_part(step.d, step.device_part(step.d))
-    step.graphs = graphs
+        step.step_eager()
     torch.cuda.synchronize()
     prof = _lib.profile_read()
     _lib.profile(False)
 
-    # HBM-bound evidence: RoIAlign forward / backward alone at cfg3 scale (8x1024x38x75, 2048 RoIs,
-    # 630 MB of algorithmic traffic per direction: larger than L2, so no flush is needed)
-    cfg3 = None
-    secondary = None
+    # cfg4 (8 images / GPU, MAF multi-level DA heads) measured after the headline, every N
+    cfg4 = None
+    if args.workload == "cfg2" and not args.no_cfg4:
+        wl4 = Workload("cfg4")
+        step.graphs = None  # release the cfg2 graphs' memory pool
+        step4 = TlodStep(dev, seed=13 + rank, wl=wl4, use_graph=not args.no_graph)
+        ms4, _, ranks4 = timed(step4.step, min(args.steps, 20), 3)
+        ms4_ar = None
+        if world > 1:
+            grads = torch.zeros(142 * 1000 * 1000, dtype=torch.float32, device=dev)
+
+            def step4_ar():
+                work = dist.all_reduce(grads, async_op=True)
+                step4.step()
+                work.wait()
+            ms4_ar, _, _ = timed(step4_ar, min(args.steps, 20), 3)
+            del grads
+        n4 = min(args.steps, 20)
+        cfg4 = {"workload": wl4.text, "images_per_gpu": 8, "rois_per_step_per_gpu": wl4.rois_per_step,
+                "value": world * wl4.rois_per_step * n4 / (ms4 * 1e-3), "unit": "RoIs/s", "ms_per_step": ms4 / n4,
+                "per_rank_ms_per_step": [v / n4 for v in ranks4],
+                "with_grad_allreduce": None if ms4_ar is None else {
+                    "value": world * wl4.rois_per_step * n4 / (ms4_ar * 1e-3), "unit": "RoIs/s",
+                    "ms_per_step": ms4_ar / n4, "allreduce_bytes": 142 * 1000 * 1000 * 4}}
+        del step4
+
+    # HBM-bound evidence and the other 8(d) metrics, rank 0 only
+    align = secondary = None
     if rank == 0 and not args.no_cfg3:
-        cfg3 = roi_align_cfg3(dev)
+        align = roi_align_sizes(dev)
         secondary = secondary_metrics(dev)
 
     if rank != 0:
@@ -511,73 +790,96 @@ def run_tlod(args):
     total_ms = sum(v[0] for v in prof.values()) or 1.0
     kernels = {k: {"ms_per_launch": v[0] / v[1], "launches": v[1], "share": v[0] / total_ms}
                for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
-    # algorithmic bytes per launch at this workload.  src and tgt
-    # launches alternate, so the per-launch mean is used.
-    #   RoIAlign fwd / bwd: feature (gradient) map once + rois + the (R, C, 8, 8) tensor once
-    #   avg-pool fwd / bwd: the (R, C, 8, 8) and the (R, C, 7, 7) tensor once each
-    def roi_bytes(n_img, n_roi):
-        return n_img * C * H * W * 4 + n_roi * 20 + n_roi * C * 64 * 4
 
-    def pool_bytes(n_roi):
-        return n_roi * C * (64 + 49) * 4
-    r_src, r_tgt = N_SRC * ROIS_SRC, N_TGT * ROIS_TGT
-    alg = {"roi_align_fwd_planes_kernel": (roi_bytes(N_SRC, r_src) + roi_bytes(N_TGT, r_tgt)) / 2.0,
-           "roi_align_bwd_rows_kernel": (roi_bytes(N_SRC, r_src) + roi_bytes(N_TGT, r_tgt)) / 2.0,
-           "avgpool2x2_fwd_kernel": (pool_bytes(r_src) + pool_bytes(r_tgt)) / 2.0,
-           "avgpool2x2_bwd_kernel": (pool_bytes(r_src) + pool_bytes(r_tgt)) / 2.0}
-    traffic = {}
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            traffic = json.load(f).get("bench_cfg2", {})
-    except Exception:  # noqa: BLE001
-        pass
-    by_kernel = {}
+    # algorithmic bytes per launch inside the step; src and tgt launches
+    # alternate, so the per-launch mean is used
+    def roi_bytes(n_img, n_roi, cells):
+        return n_img * C * H * W * 4 + n_roi * 20 + n_roi * C * cells * 4
+    r_src, r_tgt = wl.n_src * ROIS_SRC, wl.n_tgt * ROIS_TGT
+    alg = {"roi_align_avg_fwd8_kernel": (roi_bytes(wl.n_src, r_src, 49) + roi_bytes(wl.n_tgt, r_tgt, 49)) / 2.0,
+           "roi_align_bwd_rows_kernel": (roi_bytes(wl.n_src, r_src, 64) + roi_bytes(wl.n_tgt, r_tgt, 64)) / 2.0,
+           "avgpool2x2_bwd_kernel": (r_src + r_tgt) / 2.0 * C * (64 + 49) * 4}
+    traffic = load_traffic("bench_cfg2")
+    in_step = {}
     for name, nbytes in alg.items():
         if name in kernels:
             t = kernels[name]["ms_per_launch"] * 1e-3
-            by_kernel[name] = {"kernel": name, "bound": "hbm", "achieved": nbytes / t / 1e9, "peak": peak,
-                               "unit": "GB/s", "frac": nbytes / t / 1e9 / peak, "traffic": traffic.get(name),
-                               "algorithmic_bytes_per_launch": nbytes, "share_of_step": kernels[name]["share"]}
+            in_step[name] = {"kernel": name, "bound": "hbm", "achieved": nbytes / t / 1e9, "peak": peak,
+                             "unit": "GB/s", "frac": nbytes / t / 1e9 / peak, "traffic": traffic.get(name),
+                             "algorithmic_bytes_per_launch": nbytes, "share_of_step": kernels[name]["share"],
+                             "l2_resident": True}
     dominant = next(iter(kernels)) if kernels else None
-    # the roofline object describes the dominant kernel of the step (largest share of kernel time)
-    roofline = by_kernel.get(dominant)
-    if roofline is None and by_kernel:
-        roofline = max(by_kernel.values(), key=lambda r: r["share_of_step"])
-    if roofline is not None:
-        roofline = dict(roofline, peak_source=peak_src,
-                        note="cfg2 working set (~80 MB per launch) fits the 126 MB L2; L2 is flushed between steps; "
-                             "launch time measured with CUDA events around each launch (includes launch latency); "
-                             "the HBM-sized measurement is roi_align_cfg3")
+    # `roofline`: the step's dominant HBM-bound kernel, quoted on its HBM-sized launch (cfg3: 630 MB per
+    # direction, larger than the 126 MB L2), measured live above with CUDA events; the same kernel inside the
+    # cfg2 step (L2 resident, launch latency inside the event pair) is `roofline_in_step`
+    roofline = None
+    dom_roi = max(in_step.values(), key=lambda r: r["share_of_step"]) if in_step else None
+    if align is not None and "cfg3" in align:
+        key = "bwd" if (dom_roi and "bwd" in dom_roi["kernel"]) else "avg_fwd"
+        c3 = align["cfg3"][key]
+        nbytes = c3.get("algorithmic_bytes", c3.get("algorithmic_bytes_fused"))
+        roofline = {"kernel": c3["kernel"], "bound": "hbm", "achieved": nbytes / (c3["us"] * 1e-6) / 1e9,
+                    "peak": peak, "unit": "GB/s", "frac": nbytes / (c3["us"] * 1e-6) / 1e9 / peak,
+                    "traffic": c3.get("traffic"), "algorithmic_bytes_per_launch": nbytes, "l2_resident": False,
+                    "config": "cfg3 (8x1024x38x75, 2048 RoIs)", "peak_source": peak_src,
+                    "note": "HBM-sized launch of the step's dominant RoI kernel, CUDA events around back-to-back "
+                            "launches in this run; roofline_in_step has the same kernel inside the L2-resident cfg2 step"}
+    elif dom_roi is not None:
+        roofline = dict(dom_roi, peak_source=peak_src)
     h2d, d2h = step.e2e_bytes()
+    n = args.steps
     line = {
-        "metric": "RoIs/sec RoIAlign fwd+bwd & proposals/sec (12000->2000 NMS) vs HBM roofline",
-        "value": world * ROIS_PER_STEP * args.steps / (ms_dev * 1e-3),
+        "metric": METRIC,
+        "value": world * wl.rois_per_step * n / (ms_dev * 1e-3),
         "unit": "RoIs/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_dev / args.steps,
+        "n_gpus": world, "steps": n, "warmup": args.warmup,
+        "ms_per_step": ms_dev / n,
+        "per_rank_ms_per_step": {"min": min(ranks_dev) / n, "median": statistics.median(ranks_dev) / n,
+                                 "max": max(ranks_dev) / n},
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "rois_per_step_per_gpu": ROIS_PER_STEP,
-                   "proposals_per_step_per_gpu": PROPOSALS_PER_STEP, "images_per_step_per_gpu": N_SRC + N_TGT,
+        "config": {"workload": wl.text, "rois_per_step_per_gpu": wl.rois_per_step,
+                   "proposals_per_step_per_gpu": wl.proposals_per_step, "images_per_step_per_gpu": wl.n_src + wl.n_tgt,
                    "l2": "256 MB buffer zeroed between timed iterations (outside the event pairs)",
                    "parallelism": "image-sharded, %d rank(s), no data-path collective" % world},
-        "proposals_per_s": world * PROPOSALS_PER_STEP * args.steps / (ms_dev * 1e-3),
-        "e2e": {"value": world * ROIS_PER_STEP * args.steps / (ms_e2e * 1e-3), "unit": "RoIs/s",
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+        "proposals_per_s": world * wl.proposals_per_step * n / (ms_dev * 1e-3),
+        "e2e": {"value": world * wl.rois_per_step * n / (ms_e2e * 1e-3), "unit": "RoIs/s",
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / n,
+                "per_rank_ms_per_step": {"min": min(ranks_e2e) / n, "median": statistics.median(ranks_e2e) / n,
+                                         "max": max(ranks_e2e) / n},
+                "note": "H2D per step (one packed pinned arena per domain): feature maps, RPN softmax + deltas + "
+                        "head logits, im_info, gt boxes, DA-head outputs.  D2H per step (one packed arena): rois, "
+                        "sampled labels + regression targets, GRL'd feature gradients, DA + RPN losses, anchor "
+                        "labels.  NOT copied: RoIAlign's pooled output and the detection-head gradient `top` (both "
+                        "live only on the device in training), anchor bbox targets / weights (consumed by the RPN "
+                        "loss on the device)"},
         "with_grad_allreduce": None if ms_ar is None else {
-            "value": world * ROIS_PER_STEP * args.steps / (ms_ar * 1e-3), "unit": "RoIs/s",
-            "ms_per_step": ms_ar / args.steps, "allreduce_bytes": 142 * 1000 * 1000 * 4,
+            "value": world * wl.rois_per_step * n / (ms_ar * 1e-3), "unit": "RoIs/s",
+            "ms_per_step": ms_ar / n, "allreduce_bytes": 142 * 1000 * 1000 * 4,
             "note": "same step with a 568 MB fp32 NCCL all-reduce (the DP gradient exchange of the training "
-                    "loop) overlapped; outside the path, reported for BASELINE config 4"},
+                    "loop) overlapped; outside the path"},
+        "cfg4": cfg4,
         "gpu_launches": int(launches),
-        "cuda_graph": step.graph is not None,
+        "cuda_graph": used_graph,
+        "graph_check": graph_check,
         "clocks": parse_clocks(clock_file),
-        "roofline": roofline, "roofline_by_kernel": by_kernel,
-        "dominant_kernel": dominant, "kernels": kernels, "roi_align_cfg3": cfg3, "secondary": secondary,
+        "roofline": roofline, "roofline_in_step": in_step,
+        "dominant_kernel": dominant, "kernels": kernels, "roi_align": align,
+        "roi_align_cfg3": None if align is None else align.get("cfg3"), "secondary": secondary,
+        "scaling_limiter": ("none on the device path (image-sharded, no collective); e2e is bounded by the host: "
+                            "every rank moves %.1f MB H2D + %.1f MB D2H per step through the box's shared PCIe "
+                            "root / host memory, and runs its RNG-exact host sampling on its own core slice%s"
+                            % (h2d / 1e6, d2h / 1e6,
+                               "" if cores_bound is None else " (%d cores per rank)" % cores_bound)),
         "wall_s": wall,
     }
-    if not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_reference(steps=2, warmup=0, threads=os.cpu_count())
+    if not args.no_reference:
+        ref = reference_subprocess(0 if args.no_cpu_baseline else 2)
+        if "cpu_baseline" in ref:
+            line["cpu_baseline"] = ref.pop("cpu_baseline")
+        line["gpu_reference"] = ref.get("gpu_reference", ref)
+        line["cpu_as_shipped"] = ref.get("cpu_as_shipped")
+        line["speedup_vs_reference_kernels"] = speedups(ref, align, secondary)
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -586,11 +888,11 @@ def run_tlod(args):
 # ---------------------------------------------------------------------------
 # CPU arm: the oracle (C restatement of the reference's kernels + numpy host logic)
 # ---------------------------------------------------------------------------
-def cpu_step(inp, anchors, orc, half):
+def cpu_step(inp, anchors, orc, half, wl):
     """One (half) step on the CPU.  half=True: 1 source + 1 target image (bounded sample)."""
     n_rois = 0
     for dom, key, per, pre, post in (("src", "TRAIN", ROIS_SRC, 12000, 2000), ("tgt", "TEST", ROIS_TGT, 6000, 300)):
-        n = 1 if half else (N_SRC if dom == "src" else N_TGT)
+        n = 1 if half else (wl.n_src if dom == "src" else wl.n_tgt)
         feat = inp[dom + "_feat"][:n].numpy()
         rois = orc.proposal_layer(inp[dom + "_prob"][:n].numpy(), inp[dom + "_deltas"][:n].numpy(),
                                   inp[dom + "_im_info"][:n].numpy(), anchors, 16, pre, post, 0.7)
@@ -615,15 +917,16 @@ def cpu_reference(steps, warmup, threads):
     orc.build()
     orc.set_num_threads(threads)
     torch.set_num_threads(threads)
+    wl = Workload("cfg2")
     anchors = orc.generate_anchors(scales=[4, 8, 16, 32], ratios=[0.5, 1, 2]).astype(np.float32)
-    inp = synth_inputs(3)
+    inp = synth_inputs(3, wl)
     np.random.seed(3)
     for _ in range(warmup):
-        cpu_step(inp, anchors, orc, half=True)
+        cpu_step(inp, anchors, orc, True, wl)
     t0 = time.perf_counter()
     n = 0
     for _ in range(steps):
-        n += cpu_step(inp, anchors, orc, half=True)
+        n += cpu_step(inp, anchors, orc, True, wl)
     dt = time.perf_counter() - t0
     return {"value": n / dt, "unit": "RoIs/s", "cores": int(orc.num_threads()), "kind": "port",
             "sample": "%d x half step (1 src + 1 tgt image, %d RoIs): oracle C port of the reference kernels "
@@ -640,18 +943,20 @@ def run_reference(args):
     # bounded: ~1-2 s per half step -> cap the number of timed steps so the run ends in minutes
     steps_run = min(steps, 20)
     base = cpu_reference(steps=steps_run, warmup=warmup, threads=os.cpu_count())
+    wl = Workload("cfg2")
     line = {
         "impl": "reference",
-        "metric": "RoIs/sec RoIAlign fwd+bwd & proposals/sec (12000->2000 NMS) vs HBM roofline",
+        "metric": METRIC,
         "value": base["value"], "unit": "RoIs/s", "n_gpus": world, "steps": steps_run, "warmup": warmup,
         "ms_per_step": base["seconds"] / steps_run * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample_per_step": "half step: 1 src + 1 tgt image, 556 RoIs"},
+        "config": {"workload": wl.text, "sample_per_step": "half step: 1 src + 1 tgt image, 556 RoIs"},
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": base["value"], "unit": "RoIs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "the reference's CUDA path cannot load on torch 2.x (torch.utils.ffi) and its CPU RoIAlign "
-                "backward / nms_cpu are wrong (SURVEY.md 8c), so the CPU arm is the oracle port of its kernels",
+                "backward / nms_cpu are wrong (SURVEY.md 8c), so the CPU arm is the oracle port of its kernels; "
+                "the reference's own recompiled CUDA kernels are timed in the product arm's `gpu_reference`",
     }
     emit(line)
 
@@ -677,9 +982,12 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="tlod", choices=["tlod", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-cfg3", action="store_true", help="skip the cfg3-scale RoIAlign roofline section")
-    ap.add_argument("--no-graph", action="store_true", help="run the device part eagerly instead of a CUDA graph")
+    ap.add_argument("--no-reference", action="store_true", help="skip the reference-kernel subprocess")
+    ap.add_argument("--no-cfg3", action="store_true", help="skip the stand-alone roofline / secondary sections")
+    ap.add_argument("--no-cfg4", action="store_true", help="skip the cfg4 (8 images/GPU, MAF heads) companion")
+    ap.add_argument("--no-graph", action="store_true", help="run the device part eagerly instead of CUDA graphs")
     ap.add_argument("--watchdog", type=int, default=1500,
                     help="seconds after which a stuck run dumps its Python stacks and exits (0 = off)")
     args = ap.parse_args()

@@ -336,6 +336,16 @@ int tlod_anchor_targets_finalize(const float* labels, const int* argmax, const f
 int tlod_roi_gt_assign(const float* rois, int roi_stride, int roi_offset, const float* gt,
                        int gt_stride, float* max_overlaps, int* assignment, float* labels, int batch,
                        int n, int k, void* stream);
+/* HOST function (no GPU work): the fg / bg sampling of _ProposalTargetLayer
+ * (proposal_target_layer_cascade.py:140-181) on numpy's global MT19937 stream, draw for draw
+ * (np.random.permutation(fg_num), np.random.rand(k)): h_max_overlaps (batch, n) host floats ->
+ * h_keep (batch, rois_per_image) sampled candidate indices, foreground first; h_fg_count (batch).
+ * mt_key / mt_pos: numpy's legacy state (624 words + position), updated in place.
+ * TLOD_ERR_BAD_SHAPE if an image has neither fg nor bg candidates (the reference raises). */
+int tlod_proposal_sample_host(const float* h_max_overlaps, int batch, int n, int rois_per_image,
+                              int fg_rois_per_image, float fg_thresh, float bg_thresh_hi,
+                              float bg_thresh_lo, unsigned int* mt_key, int* mt_pos, int* h_keep,
+                              int* h_fg_count);
 /* keep (batch, rois_per_image) int32: sampled candidate indices, foreground first;
  * fg_count (batch) int32: rows >= fg_count[b] get label 0.  Outputs: rois_out
  * (batch, P, 5) with column 0 = image index, labels_out (batch, P), targets_out / inside_out /

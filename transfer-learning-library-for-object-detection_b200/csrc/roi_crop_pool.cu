@@ -33,7 +33,7 @@
 namespace tlod {
 
 constexpr int CP_NS = 14;   // samples per axis
-constexpr int CP_PO = 7;    // pooled size
+
 constexpr int CP_CH = 16;
 constexpr int CP_TILE_V = CP_CH * 49 * 4;  // pooled values of a (RoI, slab)
 constexpr int CP_TILE_A = CP_CH * 49;      // argmax codes

@@ -47,13 +47,23 @@ _MT_WORDS = 624
 _native_ok = None
 
 
+_mt_address = (None, None)  # (bit generator object, address of its state)
+
+
 def _numpy_mt19937_address():
-    """Address of numpy's global legacy MT19937 state (key[624], pos) or None."""
+    """Address of numpy's global legacy MT19937 state (key[624], pos) or None.  The state lives
+    inside the bit-generator object (np.random.seed / set_state rewrite it in place), so the
+    address is looked up once per bit-generator object (building the ctypes interface costs ~20 us)."""
+    global _mt_address
     try:
         bitgen = np.random.mtrand._rand._bit_generator
+        if _mt_address[0] is bitgen:
+            return _mt_address[1]
         if type(bitgen).__name__ != "MT19937":
             return None
-        return int(bitgen.ctypes.state_address)
+        addr = int(bitgen.ctypes.state_address)
+        _mt_address = (bitgen, addr)
+        return addr
     except Exception:  # noqa: BLE001 -- a numpy without the ctypes interface
         return None
 
@@ -149,7 +159,10 @@ class _AnchorTargetLayer(nn.Module):
     # work between them: begin() only launches (label kernel + a pinned D2H copy on this layer's
     # own stream), finish() waits for that copy alone -- not for whatever else the caller has
     # queued meanwhile -- runs the host-side subsampling and launches the finalize kernel.
-    def begin(self, input):
+    def begin(self, input, im_hw=None):
+        """im_hw: (height, width) of the first image in pixels if the caller already knows it on
+        the host -- the layer then does not read im_info[0] back (a blocking D2H of three floats,
+        which is what the reference's `long(im_info[0][1])` does, anchor_target_layer.py:86-87)."""
         rpn_cls_score, gt_boxes, im_info, num_boxes = input[0], input[1], input[2], input[3]
         height, width = rpn_cls_score.size(2), rpn_cls_score.size(3)
         dev = gt_boxes.device
@@ -160,20 +173,37 @@ class _AnchorTargetLayer(nn.Module):
         cur = torch.cuda.current_stream(dev)
         stream.wait_stream(cur)  # inputs produced on the caller's stream
         with torch.cuda.stream(stream):
-            # :86-87 -- the FIRST image's size, truncated to int, is used for the whole batch
-            info0 = im_info[0].tolist()
-            anchors, inds_inside, inv_index = self._inside(height, width, int(info0[1]), int(info0[0]), dev)
-            labels, argmax = F.anchor_labels(anchors, gt_boxes, cfg.TRAIN.RPN_NEGATIVE_OVERLAP,
-                                             cfg.TRAIN.RPN_POSITIVE_OVERLAP, cfg.TRAIN.RPN_CLOBBER_POSITIVES)
+            if im_hw is None:
+                # :86-87 -- the FIRST image's size, truncated to int, is used for the whole batch
+                info0 = im_info[0].tolist()
+                im_hw = (info0[0], info0[1])
+            state = self.launch_labels(gt_boxes, height, width, im_hw)
+            state["copied"] = torch.cuda.Event()
+            state["copied"].record(stream)
+            state["stream"] = stream
+        for t in (gt_boxes, im_info):
+            t.record_stream(stream)
+        return state
+
+    def launch_labels(self, gt_boxes, height, width, im_hw, labels_host=None):
+        """The device half of begin() as pure launches on the CURRENT stream (capturable in a CUDA
+        graph): IoU + label rules, and the pinned D2H copy of the labels.  labels_host: a pinned
+        (B, n) buffer owned by the caller (a graph replays into it); by default one is taken from
+        the layer's pool and returned to it by finish().  The caller of this method sets
+        state["copied"] (an event recorded after these launches) and state["stream"]."""
+        dev = gt_boxes.device
+        anchors, inds_inside, inv_index = self._inside(height, width, int(im_hw[1]), int(im_hw[0]), dev)
+        labels, argmax = F.anchor_labels(anchors, gt_boxes, cfg.TRAIN.RPN_NEGATIVE_OVERLAP,
+                                         cfg.TRAIN.RPN_POSITIVE_OVERLAP, cfg.TRAIN.RPN_CLOBBER_POSITIVES)
+        pooled = labels_host is None
+        if pooled:
             # the pinned staging buffer travels with the returned state (begin() may be called again
             # before finish(), e.g. by DataParallel replicas sharing this module's attributes)
             labels_host = self._take_pinned(dev.index, tuple(labels.shape), labels.dtype)
-            labels_host.copy_(labels, non_blocking=True)
-            copied = torch.cuda.Event()
-            copied.record(stream)
-        for t in (gt_boxes, im_info):
-            t.record_stream(stream)
-        return (labels, argmax, anchors, inv_index, gt_boxes, height, width, copied, stream, labels_host)
+        labels_host.copy_(labels, non_blocking=True)
+        return {"labels": labels, "argmax": argmax, "anchors": anchors, "inv_index": inv_index,
+                "gt_boxes": gt_boxes, "height": height, "width": width, "labels_host": labels_host,
+                "pooled": pooled, "copied": None, "stream": None}
 
     def _take_pinned(self, dev_index, shape, dtype):
         with self._pool_lock:
@@ -189,7 +219,9 @@ class _AnchorTargetLayer(nn.Module):
                 free.append(buf)
 
     def finish(self, state):
-        labels, argmax, anchors, inv_index, gt_boxes, height, width, copied, stream, labels_host = state
+        labels, argmax, anchors, inv_index = state["labels"], state["argmax"], state["anchors"], state["inv_index"]
+        gt_boxes, height, width = state["gt_boxes"], state["height"], state["width"]
+        copied, stream, labels_host = state["copied"], state["stream"], state["labels_host"]
         batch_size = gt_boxes.size(0)
         A = self._num_anchors
         copied.synchronize()
@@ -216,7 +248,8 @@ class _AnchorTargetLayer(nn.Module):
         torch.cuda.current_stream(gt_boxes.device).wait_stream(stream)
         # the upload reads the pinned buffer asynchronously: it returns to the pool only for work
         # queued on this device's side stream (begin() fills it there), which is ordered behind the upload
-        self._give_pinned(gt_boxes.device.index, labels_host)
+        if state["pooled"]:
+            self._give_pinned(gt_boxes.device.index, labels_host)
         for t in out:
             t.record_stream(torch.cuda.current_stream(gt_boxes.device))
         return list(out)

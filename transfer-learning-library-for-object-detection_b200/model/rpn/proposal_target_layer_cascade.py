@@ -17,6 +17,90 @@ from model.utils.config import cfg
 from tlod_b200 import functional as F
 
 
+_native_ok = None
+
+
+def _sample_numpy(mo, rois_per_image, fg_rois_per_image):
+    """:140-181 with numpy's own calls (what the native sampler is checked against)."""
+    B = mo.shape[0]
+    keep = np.empty((B, rois_per_image), np.int32)
+    fg_count = np.empty((B,), np.int32)
+    fg_thresh = np.float32(cfg.TRAIN.FG_THRESH)
+    bg_hi, bg_lo = np.float32(cfg.TRAIN.BG_THRESH_HI), np.float32(cfg.TRAIN.BG_THRESH_LO)
+    for i in range(B):
+        fg_inds = np.nonzero(mo[i] >= fg_thresh)[0]
+        bg_inds = np.nonzero((mo[i] < bg_hi) & (mo[i] >= bg_lo))[0]
+        fg_num, bg_num = fg_inds.shape[0], bg_inds.shape[0]
+        if fg_num > 0 and bg_num > 0:
+            fg_this = min(fg_rois_per_image, fg_num)
+            rand_num = np.random.permutation(fg_num)
+            fg_inds = fg_inds[rand_num[:fg_this]]
+            bg_this = rois_per_image - fg_this
+            rand_num = np.floor(np.random.rand(bg_this) * bg_num).astype(np.int64)
+            bg_inds = bg_inds[rand_num]
+        elif fg_num > 0 and bg_num == 0:
+            rand_num = np.floor(np.random.rand(rois_per_image) * fg_num).astype(np.int64)
+            fg_inds = fg_inds[rand_num]
+            fg_this = rois_per_image
+            bg_inds = bg_inds[:0]
+        elif bg_num > 0 and fg_num == 0:
+            rand_num = np.floor(np.random.rand(rois_per_image) * bg_num).astype(np.int64)
+            bg_inds = bg_inds[rand_num]
+            fg_this = 0
+            fg_inds = fg_inds[:0]
+        else:
+            raise ValueError("bg_num_rois = 0 and fg_num_rois = 0, this should not happen!")
+        keep[i] = np.concatenate([fg_inds, bg_inds])
+        fg_count[i] = fg_this
+    return keep, fg_count
+
+
+def _sample_native(mo, rois_per_image, fg_rois_per_image):
+    from model.rpn.anchor_target_layer import _MT_WORDS, _numpy_mt19937_address
+    import ctypes
+    from tlod_b200._lib import lib
+    B, n = mo.shape
+    keep = np.empty((B, rois_per_image), np.int32)
+    fg_count = np.empty((B,), np.int32)
+    addr = _numpy_mt19937_address()
+    with np.random.mtrand._rand._bit_generator.lock:
+        rc = lib.tlod_proposal_sample_host(mo.ctypes.data, B, n, rois_per_image, fg_rois_per_image,
+                                           float(cfg.TRAIN.FG_THRESH), float(cfg.TRAIN.BG_THRESH_HI),
+                                           float(cfg.TRAIN.BG_THRESH_LO), addr,
+                                           ctypes.cast(addr + 4 * _MT_WORDS, ctypes.POINTER(ctypes.c_int)),
+                                           keep.ctypes.data, fg_count.ctypes.data)
+    if rc != 0:
+        raise ValueError("bg_num_rois = 0 and fg_num_rois = 0, this should not happen!")
+    return keep, fg_count
+
+
+def _native_matches_numpy():
+    """One-time self check on a private copy of the stream: same samples AND same stream position."""
+    from model.rpn.anchor_target_layer import _numpy_mt19937_address
+    if _numpy_mt19937_address() is None:
+        return False
+    saved = np.random.get_state()
+    try:
+        rs = np.random.RandomState(4321)
+        mo = (rs.rand(3, 700) ** 2).astype(np.float32)
+        mo[2] = mo[2] * 0.4  # an image without foreground
+        ok = True
+        for rpi, fgr in ((256, 64), (128, 32)):
+            np.random.seed(77)
+            ka, fa = _sample_numpy(mo, rpi, fgr)
+            sa = np.random.get_state()
+            np.random.seed(77)
+            kb, fb = _sample_native(mo, rpi, fgr)
+            sb = np.random.get_state()
+            ok = ok and np.array_equal(ka, kb) and np.array_equal(fa, fb) and sa[2] == sb[2] and \
+                np.array_equal(sa[1], sb[1])
+        return bool(ok)
+    except Exception:  # noqa: BLE001
+        return False
+    finally:
+        np.random.set_state(saved)
+
+
 class _ProposalTargetLayer(nn.Module):
     def __init__(self, nclasses):
         super(_ProposalTargetLayer, self).__init__()
@@ -49,45 +133,22 @@ class _ProposalTargetLayer(nn.Module):
                 "host": host, "copied": copied}
 
     def sample(self, state):
-        """Host-side fg / bg sampling, :140-181: same index order, same RNG calls."""
+        """Host-side fg / bg sampling, :140-181: same index order, same RNG calls.  Runs the native
+        sampler (tlod_proposal_sample_host, on numpy's own MT19937 state) once it has been checked
+        against the numpy transcription below on this installation."""
+        global _native_ok
         if state["copied"] is not None:
             state["copied"].synchronize()
         mo = state["host"].numpy()
-        B = mo.shape[0]
         num_images = 1
         rois_per_image = int(cfg.TRAIN.BATCH_SIZE / num_images)
         fg_rois_per_image = int(np.round(cfg.TRAIN.FG_FRACTION * rois_per_image))
         fg_rois_per_image = 1 if fg_rois_per_image == 0 else fg_rois_per_image
-        keep = np.empty((B, rois_per_image), np.int32)
-        fg_count = np.empty((B,), np.int32)
-        fg_thresh = np.float32(cfg.TRAIN.FG_THRESH)
-        bg_hi, bg_lo = np.float32(cfg.TRAIN.BG_THRESH_HI), np.float32(cfg.TRAIN.BG_THRESH_LO)
-        for i in range(B):
-            fg_inds = np.nonzero(mo[i] >= fg_thresh)[0]
-            bg_inds = np.nonzero((mo[i] < bg_hi) & (mo[i] >= bg_lo))[0]
-            fg_num, bg_num = fg_inds.shape[0], bg_inds.shape[0]
-            if fg_num > 0 and bg_num > 0:
-                fg_this = min(fg_rois_per_image, fg_num)
-                rand_num = np.random.permutation(fg_num)
-                fg_inds = fg_inds[rand_num[:fg_this]]
-                bg_this = rois_per_image - fg_this
-                rand_num = np.floor(np.random.rand(bg_this) * bg_num).astype(np.int64)
-                bg_inds = bg_inds[rand_num]
-            elif fg_num > 0 and bg_num == 0:
-                rand_num = np.floor(np.random.rand(rois_per_image) * fg_num).astype(np.int64)
-                fg_inds = fg_inds[rand_num]
-                fg_this = rois_per_image
-                bg_inds = bg_inds[:0]
-            elif bg_num > 0 and fg_num == 0:
-                rand_num = np.floor(np.random.rand(rois_per_image) * bg_num).astype(np.int64)
-                bg_inds = bg_inds[rand_num]
-                fg_this = 0
-                fg_inds = fg_inds[:0]
-            else:
-                raise ValueError("bg_num_rois = 0 and fg_num_rois = 0, this should not happen!")
-            keep[i] = np.concatenate([fg_inds, bg_inds])
-            fg_count[i] = fg_this
-        return keep, fg_count
+        if _native_ok is None:
+            _native_ok = _native_matches_numpy()
+        if _native_ok and mo.dtype == np.float32 and mo.flags.c_contiguous:
+            return _sample_native(mo, rois_per_image, fg_rois_per_image)
+        return _sample_numpy(mo, rois_per_image, fg_rois_per_image)
 
     def finish(self, state, keep, fg_count):
         """keep (B, rois_per_image) / fg_count (B,): numpy arrays from sample(), or int32 device tensors

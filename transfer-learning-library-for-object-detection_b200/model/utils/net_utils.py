@@ -48,3 +48,17 @@ def roi_crop_max_pool(base_feat, rois, grid_size):
         return RoICropPoolFunction.apply(base_feat, grid_y.detach(), grid_x.detach())
     grid_yx = torch.stack([grid_xy[:, :, :, 1], grid_xy[:, :, :, 0]], 3).contiguous()
     return F.max_pool2d(RoICropFunction.apply(base_feat, grid_yx.detach()), 2, 2)
+
+
+def _smooth_l1_loss(bbox_pred, bbox_targets, bbox_inside_weights, bbox_outside_weights, sigma=1.0, dim=[1]):
+    """lib/model/utils/net_utils.py:72-86 (imported by the reference's rpn.py:10 and faster_rcnn.py):
+    the eager torch expression.  The fused kernel pair behind tlod_b200.rpn_losses computes the same
+    loss together with the RPN cross-entropy in one launch each way."""
+    s2 = sigma ** 2
+    diff = bbox_inside_weights * (bbox_pred - bbox_targets)
+    a = diff.abs()
+    quad = (a < 1.0 / s2).detach().float()
+    loss = bbox_outside_weights * (diff.pow(2) * (s2 / 2.0) * quad + (a - 0.5 / s2) * (1.0 - quad))
+    for i in sorted(dim, reverse=True):
+        loss = loss.sum(i)
+    return loss.mean()
