@@ -81,6 +81,9 @@ struct NmsState {
 // continues the greedy scan over those boxes.  S_1 is sized so that the scan normally reaches
 // max_keep inside phase 1 (the IoU work is then S_1^2/2 pairs instead of n^2/2); if it does
 // not, the next phase is four times larger.  Later phases find `done` set and return.
+// (Tried: merging the later phases into one -- 6000 -> 300 as 1024 | 6000 instead of 1024 | 4096 | 6000 --
+// saves two idle launches, ~5 us of 60 at IoU 0.7, but doubles the IoU work whenever phase 2 is
+// entered: the IoU-0.3 sweep at batch 64 went from 1.08 to 1.97 ms.)
 __host__ __device__ inline int nms_phase_end(int n, int max_keep, int phase /* 1-based */) {
   long long s = 2LL * max_keep;
   if (s < 1024) s = 1024;
@@ -521,14 +524,19 @@ __device__ __forceinline__ int run_lower_bound(const unsigned long long* __restr
 // the b-th block of 32 keys of the run.
 constexpr int TK_SMP = TK_RUN / 32;  // samples per run
 constexpr int TK_SMP_RUNS = 64;      // runs whose samples fit the shared-memory table
-__device__ __forceinline__ int run_lower_bound_2level(const unsigned long long* __restrict__ r,
-                                                      const unsigned long long* __restrict__ smp,
-                                                      unsigned long long key) {
-  int blk = 0;  // number of blocks whose last key is < key
+// number of 32-key blocks of a run whose last key is < key (6 steps in the shared sample table)
+__device__ __forceinline__ int run_blocks_below(const unsigned long long* __restrict__ smp, unsigned long long key) {
+  int blk = 0;
 #pragma unroll
   for (int step = TK_SMP / 2; step > 0; step >>= 1)
     if (smp[blk + step - 1] < key) blk += step;
   blk += (smp[blk] < key) ? 1 : 0;
+  return blk;
+}
+__device__ __forceinline__ int run_lower_bound_2level(const unsigned long long* __restrict__ r,
+                                                      const unsigned long long* __restrict__ smp,
+                                                      unsigned long long key) {
+  const int blk = run_blocks_below(smp, key);
   if (blk == TK_SMP) return TK_RUN;
   const unsigned long long* q = r + blk * 32;
   int lo = 0;  // keys of the block that are < key (its last key is >= key)
@@ -566,6 +574,18 @@ __global__ void __launch_bounds__(TK_THREADS)
     if (key == ~0ULL) return;   // padding
     int rank = p;
     if (two_level) {
+      // A lower bound of the rank from the shared sample tables alone (whole 32-key blocks below the
+      // key): most keys of a run cannot reach the top n_sorted (6000 or 12000 of 33300) and leave here,
+      // before any of the searches that go to L2.  Keys of a warp are neighbours in their run, so
+      // warps leave as a whole.
+      // Pays when few keys survive (TEST: 6000 of 33300, -4 us of 21); with 12000 of 33300 the extra
+      // pass costs more than it saves.
+      if (3LL * n_sorted < (long long)nruns * TK_RUN) {
+        int lb = p;
+        for (int r2 = 0; r2 < nruns; ++r2)
+          if (r2 != run) lb += 32 * run_blocks_below(smp + r2 * TK_SMP, key);
+        if (lb >= n_sorted) return;
+      }
       // independent searches, eight in flight
       int r2 = 0;
       for (; r2 + 8 <= nruns; r2 += 8) {
