@@ -474,6 +474,34 @@ def roi_align_sizes(dev):
 
         def frac(nbytes, us):
             return nbytes / (us * 1e-6) / 1e9 / peak
+
+        # the same three launches (plan, forward, backward) captured in ONE CUDA graph: device time of the
+        # sequence without the host's launch path (Python + ctypes + torch.empty per call, ~8 us each, is
+        # what bounds the back-to-back eager `plan` figure above)
+        def chain(avg):
+            pl = F.roi_align_plan(rois, x.shape, 8, 8, 1.0 / 16)
+            if avg:
+                F.roi_align_avg_forward(x, rois, 7, 7, 1.0 / 16, plan=pl)
+                return F.roi_align_avg_backward(top7, rois, x.shape, 1.0 / 16, plan=pl)
+            F.roi_align_forward(x, rois, 8, 8, 1.0 / 16, plan=pl)
+            return F.roi_align_backward(top8, rois, x.shape, 1.0 / 16, plan=pl)
+        graph_us = {}
+        for key, avg in (("graph_plan_fwd_bwd", False), ("graph_plan_avg_fwd_bwd", True)):
+            try:
+                side = torch.cuda.Stream(dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    chain(avg)
+                torch.cuda.current_stream(dev).wait_stream(side)
+                torch.cuda.synchronize()
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    keep_alive = chain(avg)
+                graph_us[key] = per_call_us(gr.replay, it)
+                del gr, keep_alive
+            except Exception as e:  # noqa: BLE001
+                graph_us[key] = None
+                sys.stderr.write("bench.py: graph timing of %s failed: %r\n" % (key, e))
         traffic = load_traffic(name)
         e = {"shape": [B, Cc, Hh, Ww, R], "l2_resident": name != "cfg3", "plan": {"us": t["plan"]},
              "fwd": {"us": t["fwd"], "kernel": "roi_align_fwd8_kernel", "algorithmic_bytes": alg8,
@@ -491,6 +519,12 @@ def roi_align_sizes(dev):
                          "frac_of_hbm_peak_op_surface_bytes": frac(alg8 + R * Cc * (64 + 49) * 4, t["avg_bwd"])},
              "rois_per_s_fwd_bwd": R / ((t["plan"] + t["fwd"] + t["bwd"]) * 1e-6),
              "frac_fwd_bwd": frac(2 * alg8, t["plan"] + t["fwd"] + t["bwd"]),
+             "graph_plan_fwd_bwd_us": graph_us["graph_plan_fwd_bwd"],
+             "frac_fwd_bwd_graph": None if not graph_us["graph_plan_fwd_bwd"] else
+             frac(2 * alg8, graph_us["graph_plan_fwd_bwd"]),
+             "graph_plan_avg_fwd_bwd_us": graph_us["graph_plan_avg_fwd_bwd"],
+             "frac_avg_fwd_bwd_fused_bytes_graph": None if not graph_us["graph_plan_avg_fwd_bwd"] else
+             frac(2 * alg7, graph_us["graph_plan_avg_fwd_bwd"]),
              "rois_per_s_avg_fwd_bwd": R / ((t["plan"] + t["avg_fwd"] + t["avg_bwd"]) * 1e-6),
              "frac_avg_fwd_bwd_fused_bytes": frac(2 * alg7, t["plan"] + t["avg_fwd"] + t["avg_bwd"])}
         out[name] = e
