@@ -296,12 +296,16 @@ class TlodStep(object):
         res["anchor_targets"] = at
         return res
 
-    def step(self, copy_in=None):
-        """copy_in (e2e mode) puts each domain's H2D copy on that domain's stream."""
+    def step(self, copy_in=None, copy_out=None):
+        """copy_in / copy_out (e2e mode) put each domain's H2D / D2H copy on that domain's stream, so
+        that the target domain's results travel back while the source domain is still computing."""
         if self.graphs is None:
             if copy_in is not None:
                 copy_in("src"), copy_in("tgt")
-            return self.step_eager()
+            r = self.step_eager()
+            if copy_out is not None:
+                copy_out("tgt", r), copy_out("src", r)
+            return r
         d = self.d
         cur = torch.cuda.current_stream(self.dev)
         s_src, s_tgt, s_side = self.streams["src"], self.streams["tgt"], self.streams["side"]
@@ -324,10 +328,14 @@ class TlodStep(object):
             self.graphs["src1"].replay()
             copied = torch.cuda.Event()
             copied.record(s_src)
+        result = {"src": dict(self.static["src2"], **self.static["src3"]), "tgt": self.static["tgt"],
+                  "anchor_targets": self.at_static}
         with torch.cuda.stream(s_tgt):
             if copy_in is not None:
                 copy_in("tgt")
             self.graphs["tgt"].replay()
+            if copy_out is not None:
+                copy_out("tgt", result)
         # host, in the reference's RNG order: anchor subsampling (inside the RPN), then the fg / bg sampling
         with torch.cuda.stream(s_side):
             at = self.anchor_target.finish(pending)
@@ -343,35 +351,48 @@ class TlodStep(object):
             self.keep_d.copy_(self.keep_h, non_blocking=True)
             self.fg_d.copy_(self.fg_h, non_blocking=True)
             self.graphs["src2"].replay()
+            if copy_out is not None:
+                s_src.wait_stream(s_side)  # the source arena also carries the RPN / DA losses and anchor labels
+                copy_out("src", result)
         for s in (s_src, s_tgt, s_side):
             cur.wait_stream(s)
-        return {"src": dict(self.static["src2"], **self.static["src3"]), "tgt": self.static["tgt"],
-                "anchor_targets": self.at_static}
+        return result
 
     # ---- end to end through host buffers ----
-    def e2e_outputs(self, r):
-        out = {"src_rois": r["src"]["rois"], "src_labels": r["src"]["labels"], "src_targets": r["src"]["targets"],
+    def e2e_outputs(self, r, dom=None):
+        src = {"src_rois": r["src"]["rois"], "src_labels": r["src"]["labels"], "src_targets": r["src"]["targets"],
                "src_gfeat": r["src"]["pool"][1], "src_losses": r["src"]["da"][0], "src_rpn_losses": r["src"]["rpn"][0],
-               "tgt_rois": r["tgt"]["rois"], "tgt_gfeat": r["tgt"]["pool"][1], "tgt_losses": r["tgt"]["da"][0],
                "anchor_labels": r["anchor_targets"][0]}
-        return out
+        tgt = {"tgt_rois": r["tgt"]["rois"], "tgt_gfeat": r["tgt"]["pool"][1], "tgt_losses": r["tgt"]["da"][0]}
+        if dom == "src":
+            return src
+        if dom == "tgt":
+            return tgt
+        return dict(src, **tgt)
 
     def step_e2e(self):
         """Same step through host buffers: each domain's inputs arrive with one H2D copy from a pinned
-        arena on that domain's stream; the results leave packed in one pinned arena with one D2H copy."""
-        r = self.step(copy_in=lambda dom: self.arena[dom].h2d())
-        outs = self.e2e_outputs(r)
+        arena on that domain's stream; each domain's results leave packed in one pinned arena with one
+        D2H copy on the same stream, as soon as that domain is done."""
         if self.out_arena is None:
-            self.out_arena = Arena(outs, self.dev, False)
-        for k, v in outs.items():
-            self.out_arena.dviews[k].copy_(v.reshape(self.out_arena.dviews[k].shape), non_blocking=True)
-        self.out_arena.d2h()
+            self.out_arena = {}
+
+        def copy_out(dom, r):
+            outs = self.e2e_outputs(r, dom)
+            if dom not in self.out_arena:
+                self.out_arena[dom] = Arena(outs, self.dev, False)
+            a = self.out_arena[dom]
+            for k, v in outs.items():
+                a.dviews[k].copy_(v.reshape(a.dviews[k].shape), non_blocking=True)
+            a.d2h()
+
+        self.step(copy_in=lambda dom: self.arena[dom].h2d(), copy_out=copy_out)
         torch.cuda.current_stream(self.dev).synchronize()
-        return self.out_arena.hviews
+        return self.out_arena
 
     def e2e_bytes(self):
         h2d = sum(a.nbytes for a in self.arena.values())
-        d2h = self.out_arena.nbytes if self.out_arena is not None else 0
+        d2h = sum(a.nbytes for a in self.out_arena.values()) if self.out_arena else 0
         return h2d, d2h
 
     def check_graph_against_eager(self):
@@ -714,7 +735,7 @@ def run_tlod(args):
     wl = Workload(args.workload)
     step = TlodStep(dev, seed=3 + rank, wl=wl, use_graph=not args.no_graph)
     used_graph = step.graphs is not None
-    graph_check = step.check_graph_against_eager()
+    graph_check = "skipped (--no-graph-check)" if args.no_graph_check else step.check_graph_against_eager()
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
 
     def barrier():
@@ -746,6 +767,34 @@ def run_tlod(args):
             ranks = [float(v.item()) for v in allv]
         return max(ranks), wall, ranks
 
+    def pcie_probe():
+        """Host <-> device copy rate of this box with ALL ranks copying at once (64 MB pinned buffers):
+        the ceiling the end-to-end number sits under when every rank moves its inputs and results."""
+        nb = 64 * 1024 * 1024
+        hbuf = torch.empty(nb, dtype=torch.uint8).pin_memory()
+        dbuf = torch.empty(nb, dtype=torch.uint8, device=dev)
+        out = {}
+        for name, fn in (("h2d", lambda: dbuf.copy_(hbuf, non_blocking=True)),
+                         ("d2h", lambda: hbuf.copy_(dbuf, non_blocking=True))):
+            fn()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(4):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            rate = 4 * nb / (a.elapsed_time(b) * 1e-3) / 1e9
+            vals = [rate]
+            if world > 1:
+                t = torch.tensor([rate], device=dev, dtype=torch.float64)
+                allv = [torch.zeros_like(t) for _ in range(world)]
+                dist.all_gather(allv, t)
+                vals = [float(v.item()) for v in allv]
+            out[name + "_GBps_per_rank_min"] = min(vals)
+            out[name + "_GBps_aggregate"] = sum(vals)
+        return out
+
     clock_file = os.path.join(ROOT, "gpurun_out", "bench_clocks_rank0.csv")
     os.makedirs(os.path.dirname(clock_file), exist_ok=True)
     sampler = clocks_sampler(clock_file) if rank == 0 else None
@@ -756,6 +805,7 @@ def run_tlod(args):
     eager_per_step = (tlod_b200.launch_count() - launches0) // (args.steps + args.warmup)
     launches = (eager_per_step + (step.launches_per_replay if used_graph else 0)) * args.steps
     ms_e2e, _, ranks_e2e = timed(step.step_e2e, args.steps, max(3, args.warmup // 2))
+    pcie = pcie_probe()
 
     # BASELINE config 4 companion: the same step while the training loop's data-parallel gradient all-reduce
     # (a VGG16-DAF sized fp32 buffer, ~570 MB, NCCL over NVLink) is in flight.  It is NOT part of the
@@ -881,6 +931,10 @@ def run_tlod(args):
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / n,
                 "per_rank_ms_per_step": {"min": min(ranks_e2e) / n, "median": statistics.median(ranks_e2e) / n,
                                          "max": max(ranks_e2e) / n},
+                "pcie": dict(pcie, copy_floor_ms_per_step=max(h2d / (pcie["h2d_GBps_per_rank_min"] * 1e6),
+                                                               d2h / (pcie["d2h_GBps_per_rank_min"] * 1e6)),
+                             note="64 MB pinned copies, all ranks at once; copy_floor = the larger of this rank's "
+                                  "H2D and D2H bytes per step at the slowest rank's rate (the two directions overlap)"),
                 "note": "H2D per step (one packed pinned arena per domain): feature maps, RPN softmax + deltas + "
                         "head logits, im_info, gt boxes, DA-head outputs.  D2H per step (one packed arena): rois, "
                         "sampled labels + regression targets, GRL'd feature gradients, DA + RPN losses, anchor "
@@ -1022,6 +1076,9 @@ def main():
     ap.add_argument("--no-cfg3", action="store_true", help="skip the stand-alone roofline / secondary sections")
     ap.add_argument("--no-cfg4", action="store_true", help="skip the cfg4 (8 images/GPU, MAF heads) companion")
     ap.add_argument("--no-graph", action="store_true", help="run the device part eagerly instead of CUDA graphs")
+    ap.add_argument("--no-graph-check", action="store_true",
+                    help="skip the graph-replay == eager-step comparison (profiling runs: keeps torch's compare "
+                         "kernels out of the launch list)")
     ap.add_argument("--watchdog", type=int, default=1500,
                     help="seconds after which a stuck run dumps its Python stacks and exits (0 = off)")
     args = ap.parse_args()
