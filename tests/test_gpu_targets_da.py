@@ -168,6 +168,32 @@ def test_da_losses_forward_backward(d):
     assert torch.allclose(p.grad, p2.grad, rtol=1e-4, atol=1e-7)
 
 
+def test_da_losses_large_map_takes_the_multi_cta_image_reduction():
+    """Above 2^16 cells the image head is reduced over many CTAs before the single-CTA instance
+    part; the three losses and both gradients still follow faster_rcnn.py:181-196."""
+    import tlod_b200
+    g = torch.Generator().manual_seed(41)
+    score = torch.randn(4, 2, 150, 300, generator=g)  # 180 000 cells
+    prob = torch.sigmoid(torch.randn(1024, 1, generator=g))
+    for d in (0, 1):
+        s = score.to(DEV).requires_grad_(True)
+        p = prob.to(DEV).requires_grad_(True)
+        img, ins, cst = tlod_b200.da_losses(s, p, d)
+        (0.1 * (img + ins + cst)).backward()
+        s2 = score.to(DEV).requires_grad_(True)
+        p2 = prob.to(DEV).requires_grad_(True)
+        lab = torch.full((4, 150, 300), d, dtype=torch.long, device=DEV)
+        ref_img = torch.nn.functional.nll_loss(torch.log_softmax(s2, 1), lab)
+        ref_ins = torch.nn.BCELoss()(p2, torch.full_like(p2, float(d)))
+        cons = torch.softmax(s2, 1)[:, d].mean().detach()
+        ref_cst = torch.nn.MSELoss(reduction="sum")(p2, cons.repeat(p2.size()))
+        (0.1 * (ref_img + ref_ins + ref_cst)).backward()
+        assert torch.allclose(img, ref_img, rtol=1e-5) and torch.allclose(ins, ref_ins, rtol=1e-5)
+        assert torch.allclose(cst, ref_cst, rtol=1e-4)
+        assert torch.allclose(s.grad, s2.grad, rtol=1e-4, atol=1e-10)
+        assert torch.allclose(p.grad, p2.grad, rtol=1e-4, atol=1e-7)
+
+
 @pytest.mark.parametrize("d,batch", [(1, 1), (0, 8)])
 def test_image_da_losses_maf_three_levels(d, batch):
     """MAF / PT-MAF: conv3 (B,2,150,300), conv4 (B,2,75,150), conv5 (B,2,37,75) heads in one launch

@@ -54,3 +54,55 @@ def test_subsample_equals_reference_transcription(B, n, p):
         xb = np.random.rand()
         assert ra == rb and np.array_equal(a, b) and xa == xb
         assert (b == 1).sum(1).max() <= 128 and ((b == 1).sum(1) + (b == 0).sum(1)).max() <= 256
+
+
+def test_numpy_fallback_paths_stay_usable(monkeypatch):
+    """The native samplers write into numpy's private MT19937 state (a contract with numpy internals);
+    when the one-time self check fails they fall back to the numpy transcriptions.  Force that fallback
+    and require the same labels / samples / stream position as the native path."""
+    from model.rpn import proposal_target_layer_cascade as ptl
+    from model.utils.config import cfg
+    rs = np.random.RandomState(7)
+    lab = rs.choice(np.array([-1.0, 0.0, 1.0], np.float32), size=(2, 5000), p=[0.1, 0.8, 0.1])
+    mo = (rs.rand(3, 900) ** 2).astype(np.float32)
+    st = {"copied": None, "host": __import__("torch").from_numpy(mo)}
+    layer = ptl._ProposalTargetLayer(9)
+    old_bs = cfg.TRAIN.BATCH_SIZE
+    cfg.TRAIN.BATCH_SIZE = 64
+    try:
+        results = []
+        for native in (True, False):
+            monkeypatch.setattr(atl, "_native_ok", native)
+            monkeypatch.setattr(ptl, "_native_ok", native)
+            a = lab.copy()
+            np.random.seed(21)
+            n_ex = atl.subsample_labels(a, 128, 256)
+            keep, fg = layer.sample(st)
+            results.append((a, n_ex, keep.copy(), fg.copy(), np.random.get_state()))
+        (a0, n0, k0, f0, s0), (a1, n1, k1, f1, s1) = results
+        assert np.array_equal(a0, a1) and n0 == n1 and np.array_equal(k0, k1) and np.array_equal(f0, f1)
+        assert s0[2] == s1[2] and np.array_equal(s0[1], s1[1])
+    finally:
+        cfg.TRAIN.BATCH_SIZE = old_bs
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_proposal_sampling_native_equals_numpy(seed):
+    """tlod_proposal_sample_host vs the numpy transcription of proposal_target_layer_cascade.py:140-181:
+    fg + bg, fg only, bg only images; permutation + rand draws; same stream position afterwards."""
+    from model.rpn import proposal_target_layer_cascade as ptl
+    r = np.random.RandomState(seed)
+    mo = (r.rand(4, 600) ** (1 + seed % 3)).astype(np.float32)
+    mo[1] *= 0.3   # no foreground
+    mo[2] = 0.9    # no background
+    for rpi, fgr in ((256, 64), (16, 4), (1, 1)):
+        np.random.seed(seed)
+        a = ptl._sample_numpy(mo, rpi, fgr)
+        sa = np.random.get_state()
+        np.random.seed(seed)
+        b = ptl._sample_native(mo, rpi, fgr)
+        sb = np.random.get_state()
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        assert sa[2] == sb[2] and np.array_equal(sa[1], sb[1])
+    with pytest.raises(ValueError):
+        ptl._sample_native(np.full((1, 10), 0.05, np.float32) * 0 - 1, 4, 1)  # neither fg nor bg

@@ -48,14 +48,16 @@ __device__ inline double block_sum(double v, double* scratch) {
 }
 
 // single CTA: the tensors are a few thousand elements (B*2*H*W ~ 22 K, R ~ 10^3)
+// pre_img: NULL, or {mean NLL, mean softmax probability of channel d} of the image head already
+// reduced by da_image_loss_fwd_kernel (maps too large for one CTA)
 __global__ void __launch_bounds__(DA_THREADS)
     da_loss_fwd_kernel(const float* __restrict__ score, const float* __restrict__ prob,
                        const float* __restrict__ label, int d, float* __restrict__ out, int B,
-                       int HW, int R) {
+                       int HW, int R, const float* __restrict__ pre_img) {
   __shared__ double scratch[DA_THREADS / 32];
   double nll = 0.0, psum = 0.0;
   const long long cells = (long long)B * HW;
-  for (long long e = threadIdx.x; e < cells; e += DA_THREADS) {
+  for (long long e = threadIdx.x; e < cells && !pre_img; e += DA_THREADS) {
     const long long b = e / HW, c = e - b * HW;
     const float s0 = __ldg(score + (b * 2) * HW + c), s1 = __ldg(score + (b * 2 + 1) * HW + c);
     const float m = fmaxf(s0, s1);
@@ -66,6 +68,10 @@ __global__ void __launch_bounds__(DA_THREADS)
   }
   nll = block_sum(nll, scratch);
   psum = block_sum(psum, scratch);
+  if (pre_img) {
+    nll = (double)__ldg(pre_img) * (double)cells;
+    psum = (double)__ldg(pre_img + 1) * (double)cells;
+  }
   const float cons = cells > 0 ? (float)(psum / (double)cells) : 0.f;
   double bce = 0.0, mse = 0.0;
   for (int r = threadIdx.x; r < R; r += DA_THREADS) {
@@ -347,21 +353,34 @@ extern "C" int tlod_grl_backward_weighted(const float* grad, const float* row_we
   return last_launch_status();
 }
 
-extern "C" size_t tlod_da_loss_workspace_bytes(void) { return 16; }
+// image-head partials of da_image_loss_fwd_kernel, then its 4 output floats
+extern "C" size_t tlod_da_loss_workspace_bytes(void) { return tlod_da_image_loss_workspace_bytes() + 16; }
+
+// maps above this many cells reduce the image head over many CTAs first (needs the workspace)
+static const long long DA_SINGLE_CTA_CELLS = 1 << 16;
 
 extern "C" int tlod_da_loss_forward(const float* img_score, const float* ins_prob,
                                     const float* ins_label, int domain_label, float* losses_out,
                                     int batch, int height, int width, int num_ins, void* workspace,
                                     size_t workspace_bytes, void* stream) {
-  (void)workspace;
-  (void)workspace_bytes;
   if (!losses_out || (batch > 0 && !img_score) || (num_ins > 0 && !ins_prob)) return TLOD_ERR_NULL_POINTER;
   if (batch < 0 || height < 0 || width < 0 || num_ins < 0 || (domain_label != 0 && domain_label != 1))
     return TLOD_ERR_BAD_SHAPE;
+  const float* pre_img = nullptr;
+  if ((long long)batch * height * width > DA_SINGLE_CTA_CELLS && workspace &&
+      workspace_bytes >= tlod_da_loss_workspace_bytes()) {
+    float* img_out = (float*)((char*)workspace + tlod_da_image_loss_workspace_bytes());
+    int rc = tlod_da_image_loss_forward(1, &img_score, nullptr, &batch, &height, &width, domain_label,
+                                        -100, img_out, workspace, tlod_da_image_loss_workspace_bytes(),
+                                        stream);
+    if (rc != TLOD_OK) return rc;
+    pre_img = img_out;
+  }
   {
     LaunchScope scope("da_loss_fwd_kernel", (cudaStream_t)stream);
     da_loss_fwd_kernel<<<1, DA_THREADS, 0, (cudaStream_t)stream>>>(
-        img_score, ins_prob, ins_label, domain_label, losses_out, batch, height * width, num_ins);
+        img_score, ins_prob, ins_label, domain_label, losses_out, batch, height * width, num_ins,
+        pre_img);
   }
   return last_launch_status();
 }

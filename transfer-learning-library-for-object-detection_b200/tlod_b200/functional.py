@@ -610,9 +610,13 @@ def da_loss_forward(img_score, ins_prob, domain_label: int, ins_label=None):
     lab = None if ins_label is None else _f32(ins_label).view(-1)
     dev = img_score.device
     out = torch.empty((4,), dtype=torch.float32, device=dev)
+    ws = None
+    if B * H * W > (1 << 16):  # large maps: the image head is reduced over many CTAs first
+        ws = _workspace(dev, int(lib.tlod_da_loss_workspace_bytes()), "da_loss")
     with torch.cuda.device(dev):
         check(lib.tlod_da_loss_forward(img_score.data_ptr(), ins_prob.data_ptr(), _ptr(lab), int(domain_label),
-                                       out.data_ptr(), B, H, W, ins_prob.numel(), None, 0, _stream(dev)),
+                                       out.data_ptr(), B, H, W, ins_prob.numel(), _ptr(ws),
+                                       0 if ws is None else ws.numel(), _stream(dev)),
               "tlod_da_loss_forward")
     return out
 
