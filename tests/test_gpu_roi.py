@@ -312,6 +312,39 @@ def test_roi_pool_invalid_image_index_and_ties():
     assert rel_err(grad, refg) <= 1e-4
 
 
+def test_roi_pool_special_values_and_kernel_variants(monkeypatch):
+    """Signed zeros, -FLT_MAX, -inf and NaN cells (the reference's strict `>` from -FLT_MAX never
+    takes a NaN, -inf or -FLT_MAX cell and keeps the first of +0 / -0), RoIs reaching over the map's
+    border and bins from 1 to 11 columns wide: the plane-resident forward and the tabulated backward
+    against the oracle, and against the generic kernels bit for bit (forward) / to rounding (backward)."""
+    from tlod_b200 import functional as F
+    B, C, H, W, R, scale = 2, 16, 37, 75, 160, 1 / 16
+    g = torch.Generator().manual_seed(97)
+    palette = torch.tensor([0.0, -0.0, 1.0, 1.0, 2.5, -3.0, -3.4028234663852886e38, float("-inf"), float("nan")])
+    feat = palette[torch.randint(0, len(palette), (B, C, H, W), generator=g)]
+    feat[:, :4] = torch.randn(B, 4, H, W, generator=g)
+    rois = edge_rois(synth_rois(R, B, 98), H, W, scale)
+    rois[0] = torch.tensor([0, -200.0, -100.0, 1500.0, 700.0])      # wider than the map: 11-column bins, clipped
+    rois[1] = torch.tensor([1, 1100.0, 500.0, 1400.0, 800.0])       # mostly outside: empty bins
+    rois[2] = torch.tensor([0, 300.0, 200.0, 310.0, 210.0])         # one cell: every bin the same cell
+    rois[3] = torch.tensor([1, 0.0, 0.0, 1199.0, 599.0])            # the whole map
+    fd, rd = feat.to(DEV), rois.to(DEV)
+    out, arg = F.roi_pool_forward(fd, rd, 7, 7, scale)
+    ref, ref_arg = orc.roi_pool_forward(feat.numpy(), rois.numpy(), 7, 7, scale)
+    assert bits_equal(out.cpu().numpy(), ref)
+    assert np.array_equal(arg.cpu().numpy(), ref_arg)
+    top = torch.randn(out.shape, generator=g)
+    grad = F.roi_pool_backward(top.to(DEV), arg, rd, feat.shape, scale)
+    refg = orc.roi_pool_backward(top.numpy(), ref_arg, rois.numpy(), feat.shape, scale)
+    assert rel_err(grad.cpu().numpy(), refg) <= 1e-4
+    monkeypatch.setenv("TLOD_DISABLE_POOL_PLANES", "1")
+    monkeypatch.setenv("TLOD_DISABLE_POOL_TAB", "1")
+    out_g, arg_g = F.roi_pool_forward(fd, rd, 7, 7, scale)
+    grad_g = F.roi_pool_backward(top.to(DEV), arg, rd, feat.shape, scale)
+    assert torch.equal(out.view(torch.int32), out_g.view(torch.int32)) and torch.equal(arg, arg_g)
+    assert rel_err(grad.cpu().numpy(), grad_g.cpu().numpy()) <= 1e-5
+
+
 def test_roi_pool_module_autograd():
     from model.roi_pooling.modules.roi_pool import _RoIPooling
     B, C, H, W, R, PH, PW, scale = POOL_CASES["vgg_conv5_7x7"]

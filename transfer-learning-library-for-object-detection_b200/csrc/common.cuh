@@ -41,6 +41,11 @@ struct LaunchScope {
   }
 };
 
+// tlod_roi_pool_forward; batch_known = false (compat_launchers.cu): `batch` is an upper bound only
+int roi_pool_forward_launch(const float* features, const float* rois, float* output, int* argmax, int batch,
+                            int channels, int height, int width, int num_rois, int pooled_h, int pooled_w,
+                            float spatial_scale, bool batch_known, cudaStream_t stream);
+
 constexpr int kWarp = 32;
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }

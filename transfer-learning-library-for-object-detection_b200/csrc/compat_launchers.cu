@@ -80,9 +80,9 @@ extern "C" int ROIPoolForwardLaucher(const float* bottom_data, const float spati
                                      const int height, const int width, const int channels,
                                      const int pooled_height, const int pooled_width, const float* bottom_rois,
                                      float* top_data, int* argmax_data, cudaStream_t stream) {
-  return tlod_roi_pool_forward(bottom_data, bottom_rois, top_data, argmax_data, max_batch(channels, height, width),
-                               channels, height, width, num_rois, pooled_height, pooled_width, spatial_scale,
-                               stream) == TLOD_OK;
+  return tlod::roi_pool_forward_launch(bottom_data, bottom_rois, top_data, argmax_data,
+                                       max_batch(channels, height, width), channels, height, width, num_rois,
+                                       pooled_height, pooled_width, spatial_scale, false, stream) == TLOD_OK;
 }
 
 extern "C" int ROIPoolBackwardLaucher(const float* top_diff, const float spatial_scale, const int batch_size,
