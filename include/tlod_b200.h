@@ -307,6 +307,17 @@ int tlod_anchor_labels(const float* anchors, const float* gt, int gt_stride, flo
  * num_examples_last = number of labels >= 0 of the LAST image (:156, stale loop variable). */
 int tlod_anchor_subsample_host(float* labels, int batch, int n, int num_fg, int rpn_batchsize,
                                unsigned int* mt_key, int* mt_pos, int* num_examples_last);
+/* HOST: MT19937 key blocks generated ahead of time, off the critical path (while the device
+ * computes the labels the sampling waits for).  ahead ((blocks + 1) * 624 words): block 0 = a copy
+ * of mt_key, block j = the key numpy will hold after j more refills.  numpy's state is not touched. */
+int tlod_mt_pregen(const unsigned int* mt_key, unsigned int* ahead, int blocks);
+/* tlod_anchor_subsample_host drawing from `ahead` (tlod_mt_pregen) instead of refilling.  The
+ * blocks are used only if block 0 still equals mt_key (nothing was drawn since tlod_mt_pregen);
+ * when they run out the stream continues in mt_key.  ahead = NULL: the plain call.  Results and
+ * the final (mt_key, mt_pos) are identical either way. */
+int tlod_anchor_subsample_host_ahead(float* labels, int batch, int n, int num_fg, int rpn_batchsize,
+                                     unsigned int* mt_key, int* mt_pos, unsigned int* ahead, int ahead_blocks,
+                                     int* num_examples_last);
 /* HOST function: out[0..n) = np.random.permutation(n) drawn from the given MT19937 state
  * (numpy's legacy RandomState: Fisher-Yates from the top, masked rejection sampling). */
 int tlod_numpy_permutation(unsigned int* mt_key, int* mt_pos, long long n, long long* out);

@@ -106,3 +106,84 @@ def test_proposal_sampling_native_equals_numpy(seed):
         assert sa[2] == sb[2] and np.array_equal(sa[1], sb[1])
     with pytest.raises(ValueError):
         ptl._sample_native(np.full((1, 10), 0.05, np.float32) * 0 - 1, 4, 1)  # neither fg nor bg
+
+
+@pytest.mark.parametrize("blocks", [0, 1, 5, 40, 400])
+def test_pregenerated_blocks_give_the_same_labels_and_stream(blocks):
+    """tlod_mt_pregen + tlod_anchor_subsample_host_ahead: key blocks generated before the labels
+    arrive.  Too few blocks (the stream continues in numpy's own key), exactly enough, far too many:
+    labels and numpy's state afterwards always equal numpy's own calls."""
+    from model.rpn import anchor_target_layer as atl
+    if not atl._native_sampler_matches_numpy():
+        pytest.skip("numpy without the ctypes MT19937 state interface")
+    rs = np.random.RandomState(5)
+    lab = rs.choice(np.array([-1.0, 0.0, 1.0], np.float32), size=(3, 9000), p=[0.2, 0.7, 0.1])
+    saved = np.random.get_state()
+    try:
+        a, b = lab.copy(), lab.copy()
+        np.random.seed(31)
+        np.random.rand(100)  # start in the middle of a key block
+        ra = atl.subsample_labels_numpy(a, 128, 256)
+        sa = np.random.get_state()
+        np.random.seed(31)
+        np.random.rand(100)
+        ahead = atl.pregenerate_stream(blocks * 624) if blocks else None
+        before = np.random.get_state()
+        if ahead is not None:
+            assert ahead.size == (blocks + 1) * 624 and np.array_equal(ahead[:624], before[1])
+        rb = atl.subsample_labels(b, 128, 256, ahead)
+        sb = np.random.get_state()
+        assert ra == rb and np.array_equal(a, b)
+        assert sa[2] == sb[2] and np.array_equal(sa[1], sb[1])
+        assert np.random.randint(0, 1 << 30) >= 0 and np.array_equal(np.random.get_state()[1], np.random.get_state()[1])
+    finally:
+        np.random.set_state(saved)
+
+
+def test_stale_pregenerated_blocks_are_ignored():
+    """Somebody draws from numpy's stream between pregenerate_stream and the subsampling: the blocks
+    no longer start at numpy's key and must not be used."""
+    from model.rpn import anchor_target_layer as atl
+    if not atl._native_sampler_matches_numpy():
+        pytest.skip("numpy without the ctypes MT19937 state interface")
+    rs = np.random.RandomState(6)
+    lab = rs.choice(np.array([-1.0, 0.0, 1.0], np.float32), size=(2, 5000), p=[0.2, 0.7, 0.1])
+    saved = np.random.get_state()
+    try:
+        a, b = lab.copy(), lab.copy()
+        np.random.seed(32)
+        np.random.rand(700)
+        ra = atl.subsample_labels_numpy(a, 128, 256)
+        sa = np.random.get_state()
+        np.random.seed(32)
+        ahead = atl.pregenerate_stream(30 * 624)
+        np.random.rand(700)  # crosses a refill: numpy's key changes
+        rb = atl.subsample_labels(b, 128, 256, ahead)
+        sb = np.random.get_state()
+        assert ra == rb and np.array_equal(a, b) and sa[2] == sb[2] and np.array_equal(sa[1], sb[1])
+    finally:
+        np.random.set_state(saved)
+
+
+def test_stream_count_blocks_of_sixteen_against_numpy_for_many_sizes():
+    """The vectorised 'count only' part of the keep-last permutation (sixteen draws at a time, blocks
+    with a position-dependent draw resolved one by one): sizes around the power-of-two epochs."""
+    from model.rpn import anchor_target_layer as atl
+    if not atl._native_sampler_matches_numpy():
+        pytest.skip("numpy without the ctypes MT19937 state interface")
+    saved = np.random.get_state()
+    try:
+        for n in (130, 257, 300, 1023, 1024, 1025, 4097, 16383, 16385, 17434, 33300):
+            lab = np.zeros((1, n), np.float32)  # all background: one permutation of n, keep 256
+            lab[0, :5] = 1.0
+            a, b = lab.copy(), lab.copy()
+            np.random.seed(n)
+            ra = atl.subsample_labels_numpy(a, 128, 256)
+            sa = np.random.get_state()
+            np.random.seed(n)
+            rb = atl.subsample_labels(b, 128, 256)
+            sb = np.random.get_state()
+            assert ra == rb and np.array_equal(a, b), n
+            assert sa[2] == sb[2] and np.array_equal(sa[1], sb[1]), n
+    finally:
+        np.random.set_state(saved)

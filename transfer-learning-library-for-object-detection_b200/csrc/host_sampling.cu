@@ -16,6 +16,10 @@
 // every other consumer of the stream sees exactly what it would have seen after the reference's
 // calls.
 #include <stdint.h>
+#include <string.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include <vector>
 
@@ -23,29 +27,60 @@
 
 namespace {
 
+// k[0..624) -> the next 624 words of the stream, in place.  Branch-free twist; neither loop
+// carries a dependency shorter than 227 words, so the host compiler vectorises both.
+static void mt_twist(uint32_t* k) {
+  const int N = 624, M = 397;
+  const uint32_t MATRIX_A = 0x9908b0dfu, UPPER = 0x80000000u, LOWER = 0x7fffffffu;
+#pragma GCC ivdep
+  for (int kk = 0; kk < N - M; ++kk) {
+    const uint32_t y = (k[kk] & UPPER) | (k[kk + 1] & LOWER);
+    k[kk] = k[kk + M] ^ (y >> 1) ^ ((0u - (y & 1u)) & MATRIX_A);
+  }
+#pragma GCC ivdep
+  for (int kk = N - M; kk < N - 1; ++kk) {
+    const uint32_t y = (k[kk] & UPPER) | (k[kk + 1] & LOWER);
+    k[kk] = k[kk + (M - N)] ^ (y >> 1) ^ ((0u - (y & 1u)) & MATRIX_A);
+  }
+  const uint32_t y = (k[N - 1] & UPPER) | (k[0] & LOWER);
+  k[N - 1] = k[M - 1] ^ (y >> 1) ^ ((0u - (y & 1u)) & MATRIX_A);
+}
+
 struct Mt19937 {
-  uint32_t* key;  // 624 words, numpy's layout
+  uint32_t* key;  // 624 words, numpy's layout: numpy's own state, or a block of `ahead`
   int pos;
+  // Key blocks generated ahead of time (tlod_mt_pregen: block 0 = numpy's key, block j = its j-th
+  // successor), consumed instead of twisting on the critical path; `home` is numpy's key, which
+  // receives the current block in writeback().
+  uint32_t* home = nullptr;
+  uint32_t* ahead_end = nullptr;
+
+  // `ahead` is used only if its block 0 still equals numpy's key (nobody drew in between)
+  static Mt19937 attach(uint32_t* numpy_key, int numpy_pos, uint32_t* ahead, int ahead_blocks) {
+    Mt19937 r{numpy_key, numpy_pos};
+    r.home = numpy_key;
+    if (ahead && ahead_blocks > 0 && memcmp(ahead, numpy_key, 624 * sizeof(uint32_t)) == 0) {
+      r.key = ahead;
+      r.ahead_end = ahead + (size_t)(ahead_blocks + 1) * 624;
+    }
+    return r;
+  }
+  void writeback() {
+    if (home && key != home) memcpy(home, key, 624 * sizeof(uint32_t));
+    key = home ? home : key;
+    ahead_end = nullptr;
+  }
 
   void refill() {
-    // branch-free twist; neither loop carries a dependency shorter than 227 words, so the host
-    // compiler vectorises both (this refill runs once per 624 draws: ~40 times per image)
-    const int N = 624, M = 397;
-    const uint32_t MATRIX_A = 0x9908b0dfu, UPPER = 0x80000000u, LOWER = 0x7fffffffu;
-    uint32_t* k = key;
-#pragma GCC ivdep
-    for (int kk = 0; kk < N - M; ++kk) {
-      const uint32_t y = (k[kk] & UPPER) | (k[kk + 1] & LOWER);
-      k[kk] = k[kk + M] ^ (y >> 1) ^ ((0u - (y & 1u)) & MATRIX_A);
-    }
-#pragma GCC ivdep
-    for (int kk = N - M; kk < N - 1; ++kk) {
-      const uint32_t y = (k[kk] & UPPER) | (k[kk + 1] & LOWER);
-      k[kk] = k[kk + (M - N)] ^ (y >> 1) ^ ((0u - (y & 1u)) & MATRIX_A);
-    }
-    const uint32_t y = (k[N - 1] & UPPER) | (k[0] & LOWER);
-    k[N - 1] = k[M - 1] ^ (y >> 1) ^ ((0u - (y & 1u)) & MATRIX_A);
     pos = 0;
+    if (ahead_end) {
+      if (key + 1248 <= ahead_end) {  // the successor was generated ahead of time
+        key += 624;
+        return;
+      }
+      writeback();  // out of blocks: go on in numpy's own memory
+    }
+    mt_twist(key);
   }
   uint32_t next32() {
     if (pos == 624) refill();
@@ -136,13 +171,21 @@ void legacy_permutation(Mt19937& rng, T* x, long long n) {
 // permutation.  Fisher-Yates from the top finalises position i in iteration i, so those entries
 // are known after the first `keep` accepted draws; the remaining n - 1 - keep iterations only have
 // to advance the stream by exactly the words numpy would have consumed (rejections included), which
-// is a streaming count over the tempered words with no random memory access.  x[n - keep .. n) holds
-// the surviving entries on return (x[0 .. n - keep) is unspecified); the stream position afterwards
-// is the one `np.random.permutation(n)` leaves.
-void legacy_permutation_keep_last(Mt19937& rng, int* x, int n, int keep) {
-  for (int i = 0; i < n; ++i) x[i] = i;
-  if (n < 2) return;
+// is a streaming count over the tempered words with no random memory access.  out[0 .. keep) receives
+// the surviving entries (the last `keep` of the permutation, in order); the stream position
+// afterwards is the one `np.random.permutation(n)` leaves.  `ident` is a per-thread identity array
+// (ident[i] == i between calls): only the <= 2 * keep entries the swaps touch are written and put
+// back, instead of initialising n entries per call.
+void legacy_permutation_keep_last(Mt19937& rng, std::vector<int>& ident, std::vector<int>& touched, int n,
+                                  int keep, int* out) {
+  for (int i = (int)ident.size(); i < n; ++i) ident.push_back(i);
+  int* x = ident.data();
   if (keep > n) keep = n;
+  if (n < 2) {
+    for (int k = 0; k < keep; ++k) out[k] = n - keep + k;
+    return;
+  }
+  touched.clear();
   const uint32_t thr = (uint32_t)(n - 1 - keep);  // iterations i > thr swap; i <= thr only count
   uint32_t i = (uint32_t)(n - 1);
   uint32_t mask = i;
@@ -173,6 +216,7 @@ void legacy_permutation_keep_last(Mt19937& rng, int* x, int n, int keep) {
       const int a = x[i], b = x[j];
       x[i] = b;
       x[j] = a;
+      touched.push_back((int)j);
       i -= acc;
     }
     while (q < avail && i >= 1) {  // stream position only: one epoch of constant mask at a time
@@ -181,13 +225,47 @@ void legacy_permutation_keep_last(Mt19937& rng, int* x, int n, int keep) {
       const uint32_t m = mask;
       uint32_t ii = i;
       int qq = q;
-      while (qq < avail && ii > floor_i) ii -= (block[qq++] & m) <= ii;
+      // Sixteen draws at a time: draw t is accepted iff v_t <= i_t, and i_t lies in [ii - 16, ii]
+      // for every t of the block, so v <= ii - 16 is an acceptance and v > ii a rejection whatever
+      // came before.  Only a draw in between (16 of ~2^14 values) depends on its predecessors: such
+      // a block is resolved one draw at a time.  The counting loop has no carried dependency and
+      // vectorises; the scalar loop it replaces was a 3-cycle chain per draw, ~40 us per image.
+      while (qq + 16 <= avail && ii > floor_i + 16) {
+        const uint32_t lo = ii - 16;
+        uint32_t sure = 0, unsure = 0;
+#if defined(__SSE2__)
+        // all values are below 2^31 (n is an int): signed compares
+        const __m128i vm = _mm_set1_epi32((int)m), vlo = _mm_set1_epi32((int)lo), vii = _mm_set1_epi32((int)ii);
+        int above_lo = 0, above_ii = 0;
+        for (int t = 0; t < 4; ++t) {
+          const __m128i v = _mm_and_si128(_mm_loadu_si128(reinterpret_cast<const __m128i*>(block + qq + 4 * t)), vm);
+          above_lo |= _mm_movemask_ps(_mm_castsi128_ps(_mm_cmpgt_epi32(v, vlo))) << (4 * t);
+          above_ii |= _mm_movemask_ps(_mm_castsi128_ps(_mm_cmpgt_epi32(v, vii))) << (4 * t);
+        }
+        sure = 16u - (uint32_t)__builtin_popcount((unsigned)above_lo);
+        unsure = (uint32_t)(above_lo & ~above_ii);
+#else
+        for (int t = 0; t < 16; ++t) {
+          const uint32_t v = block[qq + t] & m;
+          sure += v <= lo;
+          unsure += (v > lo) & (v <= ii);
+        }
+#endif
+        if (unsure) break;
+        ii -= sure;
+        qq += 16;
+      }
+      const int lim = qq + 16 < avail ? qq + 16 : avail;
+      while (qq < lim && ii > floor_i) ii -= (block[qq++] & m) <= ii;
       i = ii;
       q = qq;
     }
     rng.pos += q - at;
     at = q;
   }
+  for (int k = 0; k < keep; ++k) out[k] = x[n - keep + k];
+  for (int j : touched) x[j] = j;
+  for (int k = n - keep; k < n; ++k) x[k] = k;
 }
 
 }  // namespace
@@ -201,51 +279,75 @@ extern "C" int tlod_numpy_permutation(unsigned int* mt_key, int* mt_pos, long lo
   return TLOD_OK;
 }
 
+extern "C" int tlod_mt_pregen(const unsigned int* mt_key, unsigned int* ahead, int blocks) {
+  if (!mt_key || !ahead) return TLOD_ERR_NULL_POINTER;
+  if (blocks < 0) return TLOD_ERR_BAD_SHAPE;
+  memcpy(ahead, mt_key, 624 * sizeof(uint32_t));
+  for (int j = 0; j < blocks; ++j) {
+    uint32_t* next = ahead + (size_t)(j + 1) * 624;
+    memcpy(next, next - 624, 624 * sizeof(uint32_t));
+    mt_twist(next);
+  }
+  return TLOD_OK;
+}
+
 extern "C" int tlod_anchor_subsample_host(float* labels, int batch, int n, int num_fg, int rpn_batchsize,
                                           unsigned int* mt_key, int* mt_pos, int* num_examples_last) {
+  return tlod_anchor_subsample_host_ahead(labels, batch, n, num_fg, rpn_batchsize, mt_key, mt_pos, nullptr, 0,
+                                          num_examples_last);
+}
+
+extern "C" int tlod_anchor_subsample_host_ahead(float* labels, int batch, int n, int num_fg, int rpn_batchsize,
+                                                unsigned int* mt_key, int* mt_pos, unsigned int* ahead,
+                                                int ahead_blocks, int* num_examples_last) {
   if (!labels || !mt_key || !mt_pos || !num_examples_last) return TLOD_ERR_NULL_POINTER;
-  if (batch <= 0 || n < 0 || *mt_pos < 0 || *mt_pos > 624) return TLOD_ERR_BAD_SHAPE;
-  Mt19937 rng{mt_key, *mt_pos};
-  std::vector<int> fg, bg, perm;
-  fg.reserve(n);
-  bg.resize(n);
-  perm.reserve(n);
+  if (batch <= 0 || n < 0 || *mt_pos < 0 || *mt_pos > 624 || ahead_blocks < 0) return TLOD_ERR_BAD_SHAPE;
+  Mt19937 rng = Mt19937::attach(mt_key, *mt_pos, ahead, ahead_blocks);
+  // scratch kept per thread: three 70 KB vectors allocated and freed per call made glibc trim and
+  // regrow the heap every time (~50 page faults, more than the scan below costs)
+  static thread_local std::vector<int> fg, bg, ident, touched, kept;
+  if ((int)fg.size() < n) fg.resize(n);
+  if ((int)bg.size() < n) bg.resize(n);
   int examples = 0;
   for (int i = 0; i < batch; ++i) {
     float* lab = labels + (size_t)i * n;
     // one pass: the foreground subsampling only turns 1 into -1, so the background list
     // (labels == 0) can be collected before it
-    fg.clear();
-    int n_bg = 0;
-    int* bgp = bg.data();
+    int n_bg = 0, n_fg = 0;
+    int* __restrict__ bgp = bg.data();
+    int* __restrict__ fgp = fg.data();
+    // branch-free compaction of both lists, on the bit patterns (+-0.0 and 1.0f: an integer compare is
+    // a third of the instructions of the NaN-aware float one)
+    const uint32_t* __restrict__ bits = reinterpret_cast<const uint32_t*>(lab);
     for (int k = 0; k < n; ++k) {
-      const float v = lab[k];
+      const uint32_t v = bits[k];
       bgp[n_bg] = k;
-      n_bg += v == 0.f;
-      if (v == 1.f) fg.push_back(k);
+      n_bg += (v << 1) == 0u;
+      fgp[n_fg] = k;
+      n_fg += v == 0x3f800000u;
     }
-    int n_fg = (int)fg.size();
     if (n_fg > num_fg) {  // :124-132: disable perm[:n_fg - num_fg] = keep the last num_fg entries
-      perm.resize(n_fg);
       const int keep = num_fg > 0 ? num_fg : 0;
-      legacy_permutation_keep_last(rng, perm.data(), n_fg, keep);
+      kept.resize(keep);
+      legacy_permutation_keep_last(rng, ident, touched, n_fg, keep, kept.data());
       for (int k = 0; k < n_fg; ++k) lab[fg[k]] = -1.f;
-      for (int k = n_fg - keep; k < n_fg; ++k) lab[fg[perm[k]]] = 1.f;
+      for (int k = 0; k < keep; ++k) lab[fg[kept[k]]] = 1.f;
       n_fg = num_fg;
     }
     const int num_bg = rpn_batchsize - n_fg;  // :135
     int bg_kept = n_bg;
     if (n_bg > num_bg) {  // :138-145
-      perm.resize(n_bg);
       const int keep = num_bg > 0 ? num_bg : 0;
-      legacy_permutation_keep_last(rng, perm.data(), n_bg, keep);
+      kept.resize(keep);
+      legacy_permutation_keep_last(rng, ident, touched, n_bg, keep, kept.data());
       for (int k = 0; k < n_bg; ++k) lab[bgp[k]] = -1.f;
-      for (int k = n_bg - keep; k < n_bg; ++k) lab[bgp[perm[k]]] = 0.f;
+      for (int k = 0; k < keep; ++k) lab[bgp[kept[k]]] = 0.f;
       bg_kept = keep;
     }
     // :156 -- the LAST image's count of labels >= 0 (stale loop variable in the reference)
     examples = n_fg + bg_kept;
   }
+  rng.writeback();
   *mt_pos = rng.pos;
   *num_examples_last = examples;
   return TLOD_OK;
@@ -265,9 +367,9 @@ extern "C" int tlod_proposal_sample_host(const float* max_overlaps, int batch, i
   if (!max_overlaps || !mt_key || !mt_pos || !keep_out || !fg_count_out) return TLOD_ERR_NULL_POINTER;
   if (batch <= 0 || n < 0 || rois_per_image <= 0 || *mt_pos < 0 || *mt_pos > 624) return TLOD_ERR_BAD_SHAPE;
   Mt19937 rng{mt_key, *mt_pos};
-  std::vector<int> fg, bg, perm;
-  fg.reserve(n);
-  bg.reserve(n);
+  static thread_local std::vector<int> fg, bg, perm;
+  if ((int)fg.capacity() < n) fg.reserve(n);
+  if ((int)bg.capacity() < n) bg.reserve(n);
   auto rand_index = [&](int num) {  // floor(np.random.rand() * num)
     const uint32_t a = rng.next32() >> 5, b = rng.next32() >> 6;
     const double u = ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;

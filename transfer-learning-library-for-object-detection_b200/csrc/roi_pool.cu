@@ -404,6 +404,7 @@ __global__ void __launch_bounds__(256)
 // (the four exact divisions per row / column) instead of once per output (four per output).
 // tab[h] = phstart | phend << 8 (an empty range for rows outside the RoI), tab[H + w] likewise.
 constexpr int RPB_TAB = 1024;  // H + W served by the table kernel
+constexpr int RPB_ITER = 8;    // outputs per thread: pool_grid() gives a CTA at most 2048
 template <int PHT, int PWT>
 __global__ void __launch_bounds__(256)
     roi_pool_bwd_tab_kernel(const float* __restrict__ top_grad, const int* __restrict__ argmax,
@@ -415,6 +416,23 @@ __global__ void __launch_bounds__(256)
   const int c0 = blockIdx.y * chans_per_block;
   const PoolRoi g = pool_roi(rois + (size_t)n * 5, scale, PH, PW);
   if (g.batch < 0 || g.batch >= B) return;
+  const int S = PH * PW;
+  const int cb = min(chans_per_block, C - c0);
+  const size_t roi_base = ((size_t)n * C + c0) * S;
+  // all of this thread's argmax / gradient pairs are requested before the table is built: one
+  // memory latency per thread instead of two per output (pool_grid: at most RPB_ITER passes)
+  int idx[RPB_ITER];
+  float tg[RPB_ITER];
+#pragma unroll
+  for (int j = 0; j < RPB_ITER; ++j) {
+    const int o = threadIdx.x + j * 256;
+    idx[j] = -1;
+    tg[j] = 0.f;
+    if (o < cb * S) {
+      idx[j] = __ldg(argmax + roi_base + o);
+      tg[j] = __ldg(top_grad + roi_base + o);
+    }
+  }
   for (int t = threadIdx.x; t < H + W; t += blockDim.x) {
     const bool row = t < H;
     const int p = row ? t : t - H;
@@ -427,27 +445,25 @@ __global__ void __launch_bounds__(256)
     tab[t] = (p >= lo && p <= hi) ? (unsigned short)(s | (e << 8)) : (unsigned short)1;
   }
   __syncthreads();
-  const int S = PH * PW;
-  const int cb = min(chans_per_block, C - c0);
-  const size_t roi_base = ((size_t)n * C + c0) * S;
   const int HW = H * W;
   const int plane0 = (g.batch * C + c0) * HW;
-  for (int o = threadIdx.x; o < cb * S; o += blockDim.x) {
-    const int idx = __ldg(argmax + roi_base + o);
+#pragma unroll
+  for (int j = 0; j < RPB_ITER; ++j) {
+    const int o = threadIdx.x + j * 256;
     const int c = o / S;
     const int i = o - c * S;
     const int ph = i / PW, pw = i - ph * PW;
     // the reference's thread for cell `idx` looks only at RoIs of its own image (:150) and at
     // argmax entries of its own channel (:189): idx must lie in the plane of (image, channel)
-    const int rem = idx - plane0 - c * HW;
-    if (rem < 0 || rem >= HW) continue;
+    const int rem = idx[j] - plane0 - c * HW;
+    if (idx[j] < 0 || rem < 0 || rem >= HW) continue;
     int h = __float2int_rz(__fmul_rn((float)rem, inv_w));  // rem < 2^24: off by at most one
     int w = rem - h * W;
     if (w < 0) { --h; w += W; }
     if (w >= W) { ++h; w -= W; }
     const unsigned th = tab[h], tw = tab[H + w];
     if (ph < (int)(th & 255u) || ph >= (int)(th >> 8) || pw < (int)(tw & 255u) || pw >= (int)(tw >> 8)) continue;
-    atomicAdd(bottom_grad + idx, __ldg(top_grad + roi_base + o));
+    atomicAdd(bottom_grad + idx[j], tg[j]);
   }
 }
 
@@ -529,6 +545,7 @@ extern "C" int tlod_roi_pool_backward(const float* top_grad, const int* argmax, 
   int cpb;
   dim3 grid = pool_grid(num_rois, channels, pooled_h * pooled_w, &cpb);
   if (height + width <= RPB_TAB && pooled_h <= 255 && pooled_w <= 255 && height * width < (1 << 24) &&
+      cpb * pooled_h * pooled_w <= 256 * RPB_ITER &&
       !getenv("TLOD_DISABLE_POOL_TAB")) {
     LaunchScope scope("roi_pool_bwd_tab_kernel", st);
     auto kern = (pooled_h == 7 && pooled_w == 7) ? roi_pool_bwd_tab_kernel<7, 7> : roi_pool_bwd_tab_kernel<0, 0>;

@@ -68,15 +68,35 @@ def _numpy_mt19937_address():
         return None
 
 
-def _subsample_native(lab, num_fg, rpn_batchsize):
+def _subsample_native(lab, num_fg, rpn_batchsize, ahead=None):
     addr = _numpy_mt19937_address()
     nex = ctypes.c_int(0)
     with np.random.mtrand._rand._bit_generator.lock:
-        check(lib.tlod_anchor_subsample_host(lab.ctypes.data, lab.shape[0], lab.shape[1], int(num_fg),
-                                             int(rpn_batchsize), addr,
-                                             ctypes.cast(addr + 4 * _MT_WORDS, ctypes.POINTER(ctypes.c_int)),
-                                             ctypes.byref(nex)), "tlod_anchor_subsample_host")
+        check(lib.tlod_anchor_subsample_host_ahead(
+            lab.ctypes.data, lab.shape[0], lab.shape[1], int(num_fg), int(rpn_batchsize), addr,
+            ctypes.cast(addr + 4 * _MT_WORDS, ctypes.POINTER(ctypes.c_int)),
+            None if ahead is None else ahead.ctypes.data, 0 if ahead is None else ahead.size // _MT_WORDS - 1,
+            ctypes.byref(nex)), "tlod_anchor_subsample_host_ahead")
     return int(nex.value)
+
+
+def pregenerate_stream(words, out=None):
+    """MT19937 key blocks for about `words` future draws of numpy's global stream, generated now
+    (tlod_mt_pregen) so that subsample_labels(..., ahead=...) does not have to while the step waits
+    for it.  numpy's state is not touched; the blocks are ignored if anything draws from the stream
+    before they are used.  Returns a uint32 array ((blocks + 1) * 624) or None (no native sampler)."""
+    global _native_ok
+    if _native_ok is None:
+        _native_ok = _native_sampler_matches_numpy()
+    if not _native_ok:
+        return None
+    blocks = max(1, -(-int(words) // _MT_WORDS))
+    if out is None or out.size < (blocks + 1) * _MT_WORDS:
+        out = np.empty((blocks + 1) * _MT_WORDS, np.uint32)
+    ahead = out[:(blocks + 1) * _MT_WORDS]
+    with np.random.mtrand._rand._bit_generator.lock:
+        check(lib.tlod_mt_pregen(_numpy_mt19937_address(), ahead.ctypes.data, blocks), "tlod_mt_pregen")
+    return ahead
 
 
 def _native_sampler_matches_numpy():
@@ -102,7 +122,7 @@ def _native_sampler_matches_numpy():
         np.random.set_state(saved)
 
 
-def subsample_labels(lab, num_fg, rpn_batchsize):
+def subsample_labels(lab, num_fg, rpn_batchsize, ahead=None):
     """The random subsampling of anchor_target_layer.py:118-145 on the host copy of the labels,
     consuming numpy's global stream exactly like the reference.  Runs the native sampler
     (tlod_anchor_subsample_host, ~4x faster than numpy's shuffle: this loop is the longest host
@@ -111,7 +131,7 @@ def subsample_labels(lab, num_fg, rpn_batchsize):
     if _native_ok is None:
         _native_ok = _native_sampler_matches_numpy()
     if _native_ok and lab.dtype == np.float32 and lab.flags.c_contiguous:
-        return _subsample_native(lab, num_fg, rpn_batchsize)
+        return _subsample_native(lab, num_fg, rpn_batchsize, ahead)
     return subsample_labels_numpy(lab, num_fg, rpn_batchsize)
 
 
@@ -128,6 +148,7 @@ class _AnchorTargetLayer(nn.Module):
         self._streams = {}      # device index -> side stream of this layer
         self._pinned_pool = {}  # (device index, shape, dtype) -> free pinned staging buffers
         self._pool_lock = threading.Lock()
+        self._ahead = threading.local()  # scratch for pregenerate_stream
 
     def _inside(self, feat_h, feat_w, lim_w, lim_h, device):
         """Inside-image anchors for this map size (:66-91): (anchors (n,4), inds (n,), inverse (total,))."""
@@ -224,12 +245,18 @@ class _AnchorTargetLayer(nn.Module):
         copied, stream, labels_host = state["copied"], state["stream"], state["labels_host"]
         batch_size = gt_boxes.size(0)
         A = self._num_anchors
+        # while the device still computes the labels: the MT19937 blocks the subsampling will draw
+        # from (a permutation of the ~n background anchors per image, 1.33 words per draw on average)
+        scratch = self._ahead  # per thread: DataParallel replicas share this module's attributes
+        ahead = pregenerate_stream(1.4 * labels_host.numel(), getattr(scratch, "buf", None))
+        if ahead is not None:
+            scratch.buf = ahead.base if ahead.base is not None else ahead
         copied.synchronize()
         lab = labels_host.numpy()  # (B, n) fp32 in {-1, 0, 1}: edited in place on the host
 
         # ---- host-side subsampling, :118-145: same index order, same RNG draws ----
         num_fg = int(cfg.TRAIN.RPN_FG_FRACTION * cfg.TRAIN.RPN_BATCHSIZE)
-        num_examples = subsample_labels(lab, num_fg, cfg.TRAIN.RPN_BATCHSIZE)
+        num_examples = subsample_labels(lab, num_fg, cfg.TRAIN.RPN_BATCHSIZE, ahead)
 
         inside_w = cfg.TRAIN.RPN_BBOX_INSIDE_WEIGHTS[0]
         if cfg.TRAIN.RPN_POSITIVE_WEIGHT < 0:

@@ -65,6 +65,9 @@ SIGNATURES = {
                                    P, c_size_t, P]),
     "tlod_anchor_subsample_host": (c_int, [P, c_int, c_int, c_int, c_int, P, ctypes.POINTER(c_int),
                                            ctypes.POINTER(c_int)]),
+    "tlod_anchor_subsample_host_ahead": (c_int, [P, c_int, c_int, c_int, c_int, P, ctypes.POINTER(c_int), P, c_int,
+                                                 ctypes.POINTER(c_int)]),
+    "tlod_mt_pregen": (c_int, [P, P, c_int]),
     "tlod_numpy_permutation": (c_int, [P, ctypes.POINTER(c_int), c_longlong, P]),
     "tlod_anchor_targets_finalize": (c_int, [P, P, P, P, c_int, P, P, P, P, P, c_int, c_int, c_int, c_int,
                                              c_int, c_int, c_float, c_float, c_float, P]),
