@@ -336,12 +336,10 @@ class TlodStep(object):
             self.graphs["tgt"].replay()
             if copy_out is not None:
                 copy_out("tgt", result)
-        # host, in the reference's RNG order: anchor subsampling (inside the RPN), then the fg / bg sampling
-        with torch.cuda.stream(s_side):
-            at = self.anchor_target.finish(pending)
-            for dst, src in zip(self.at_static, at):
-                dst.copy_(src, non_blocking=True)
-            self.graphs["src3"].replay()
+        # host, in the reference's RNG order: anchor subsampling (inside the RPN), then the fg / bg sampling.
+        # The longest device chain (src2: RoIAlignAvg forward + backward on the sampled RoIs) is queued
+        # before the anchor targets' upload / finalize / RPN losses, which are short and run beside it.
+        pending = self.anchor_target.finish_host(pending)
         st = self.static["src1"][1]
         st["copied"] = copied
         keep, fg = self.proposal_target.sample(st)
@@ -351,6 +349,12 @@ class TlodStep(object):
             self.keep_d.copy_(self.keep_h, non_blocking=True)
             self.fg_d.copy_(self.fg_h, non_blocking=True)
             self.graphs["src2"].replay()
+        with torch.cuda.stream(s_side):
+            at = self.anchor_target.finish_device(pending)
+            for dst, src in zip(self.at_static, at):
+                dst.copy_(src, non_blocking=True)
+            self.graphs["src3"].replay()
+        with torch.cuda.stream(s_src):
             if copy_out is not None:
                 s_src.wait_stream(s_side)  # the source arena also carries the RPN / DA losses and anchor labels
                 copy_out("src", result)

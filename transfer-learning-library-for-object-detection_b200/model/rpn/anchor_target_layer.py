@@ -240,11 +240,13 @@ class _AnchorTargetLayer(nn.Module):
                 free.append(buf)
 
     def finish(self, state):
-        labels, argmax, anchors, inv_index = state["labels"], state["argmax"], state["anchors"], state["inv_index"]
-        gt_boxes, height, width = state["gt_boxes"], state["height"], state["width"]
-        copied, stream, labels_host = state["copied"], state["stream"], state["labels_host"]
-        batch_size = gt_boxes.size(0)
-        A = self._num_anchors
+        return self.finish_device(self.finish_host(state))
+
+    def finish_host(self, state):
+        """The host half of finish(): waits for the labels and subsamples them on numpy's stream.
+        A caller with more host work that has to follow in the reference's RNG order (the
+        proposal-target sampling) can do it before finish_device() queues the upload."""
+        copied, labels_host = state["copied"], state["labels_host"]
         # while the device still computes the labels: the MT19937 blocks the subsampling will draw
         # from (a permutation of the ~n background anchors per image, 1.33 words per draw on average)
         scratch = self._ahead  # per thread: DataParallel replicas share this module's attributes
@@ -256,8 +258,14 @@ class _AnchorTargetLayer(nn.Module):
 
         # ---- host-side subsampling, :118-145: same index order, same RNG draws ----
         num_fg = int(cfg.TRAIN.RPN_FG_FRACTION * cfg.TRAIN.RPN_BATCHSIZE)
-        num_examples = subsample_labels(lab, num_fg, cfg.TRAIN.RPN_BATCHSIZE, ahead)
+        state["num_examples"] = subsample_labels(lab, num_fg, cfg.TRAIN.RPN_BATCHSIZE, ahead)
+        return state
 
+    def finish_device(self, state):
+        labels, argmax, anchors, inv_index = state["labels"], state["argmax"], state["anchors"], state["inv_index"]
+        gt_boxes, height, width = state["gt_boxes"], state["height"], state["width"]
+        stream, labels_host, num_examples = state["stream"], state["labels_host"], state["num_examples"]
+        A = self._num_anchors
         inside_w = cfg.TRAIN.RPN_BBOX_INSIDE_WEIGHTS[0]
         if cfg.TRAIN.RPN_POSITIVE_WEIGHT < 0:
             # :155-158 -- num_examples of the LAST image (stale loop variable) for every image
