@@ -167,7 +167,13 @@ class TlodStep(object):
             self.pooled_grad = {dom: torch.randn(r, 4096, generator=g).to(dev)
                                 for dom, r in (("src", wl.n_src * ROIS_SRC), ("tgt", wl.n_tgt * ROIS_TGT))}
         self.num_boxes = torch.full((wl.n_src,), 20, dtype=torch.long)
-        self.streams = {k: torch.cuda.Stream(dev) for k in ("src", "tgt", "side")}
+        # the source chain (labels -> host sampling -> RoI work) is the critical path: its streams, and the
+        # graphs captured for them, get the higher priority; the target domain fills the gaps
+        prio = {"src": -1, "side": -1, "tgt": 0}
+        if os.environ.get("TLOD_BENCH_FLAT_PRIORITY"):
+            prio = {k: 0 for k in prio}
+        self.streams = {k: torch.cuda.Stream(dev, priority=p) for k, p in prio.items()}
+        self.capture_streams = {k: torch.cuda.Stream(dev, priority=p) for k, p in prio.items()}
         # static buffers of the proposal-target hand-over (graph mode replays into / out of them)
         self.pt_host = torch.empty((wl.n_src, 2000 + 50), dtype=torch.float32).pin_memory()
         self.keep_d = torch.zeros((wl.n_src, ROIS_SRC), dtype=torch.int32, device=dev)
@@ -260,20 +266,28 @@ class TlodStep(object):
             graphs = {}
             n0 = self.tlod.launch_count()
             graphs["at1"] = torch.cuda.CUDAGraph()   # anchor labels + their pinned D2H copy
-            with torch.cuda.graph(graphs["at1"]):
+            with torch.cuda.graph(graphs["at1"], stream=self.capture_streams["side"]):
                 self.static["at1"] = self.anchor_target.launch_labels(self.d["src_gt"], H, W, (600, 1200),
                                                                       labels_host=self.at_host)
             graphs["src1"] = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graphs["src1"]):
+            with torch.cuda.graph(graphs["src1"], stream=self.capture_streams["src"]):
                 self.static["src1"] = self.src1(self.d)
             graphs["src2"] = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graphs["src2"]):
+            with torch.cuda.graph(graphs["src2"], stream=self.capture_streams["src"]):
+                self.keep_d.copy_(self.keep_h, non_blocking=True)
+                self.fg_d.copy_(self.fg_h, non_blocking=True)
                 self.static["src2"] = self.src2(self.d, self.static["src1"][1], self.keep_d, self.fg_d)
+            # src3 starts with the anchor targets' device half: upload of the subsampled labels and of
+            # the three weights (written into this pinned tensor before every replay), finalize kernel
+            self.at_weights = torch.zeros(3, dtype=torch.float32).pin_memory()
+            self.at_weights_np, self.keep_np, self.fg_np = self.at_weights.numpy(), self.keep_h.numpy(), self.fg_h.numpy()
+            self.events = {"src1": torch.cuda.Event(), "at1": torch.cuda.Event()}
             graphs["src3"] = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graphs["src3"]):
+            with torch.cuda.graph(graphs["src3"], stream=self.capture_streams["side"]):
+                self.at_static = self.anchor_target.launch_finalize(self.static["at1"], self.at_weights)
                 self.static["src3"] = self.src3(self.d, self.at_static)
             graphs["tgt"] = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graphs["tgt"]):
+            with torch.cuda.graph(graphs["tgt"], stream=self.capture_streams["tgt"]):
                 self.static["tgt"] = self.tgt(self.d)
             self.launches_per_replay = int(self.tlod.launch_count() - n0)
             torch.cuda.synchronize(self.dev)
@@ -317,17 +331,18 @@ class TlodStep(object):
                 arrived = torch.cuda.Event()
                 arrived.record(s_src)
                 s_side.wait_event(arrived)  # the anchor-target layer reads inputs this copy delivers
-        # the anchor-target layer goes first: its label kernels + pinned D2H head the host chain
+        # two chains feed the host sampling: proposals + IoU (src1, ~150 us of device time) and the anchor
+        # labels (at1, ~35 us, then ~90 us of host subsampling): the longer device chain is queued first
+        with torch.cuda.stream(s_src):
+            self.graphs["src1"].replay()
+            copied = self.events["src1"]
+            copied.record(s_src)
         with torch.cuda.stream(s_side):
             self.graphs["at1"].replay()
             pending = self.static["at1"]
-            pending["copied"] = torch.cuda.Event()
+            pending["copied"] = self.events["at1"]
             pending["copied"].record(s_side)
             pending["stream"] = s_side
-        with torch.cuda.stream(s_src):
-            self.graphs["src1"].replay()
-            copied = torch.cuda.Event()
-            copied.record(s_src)
         result = {"src": dict(self.static["src2"], **self.static["src3"]), "tgt": self.static["tgt"],
                   "anchor_targets": self.at_static}
         with torch.cuda.stream(s_tgt):
@@ -343,21 +358,20 @@ class TlodStep(object):
         st = self.static["src1"][1]
         st["copied"] = copied
         keep, fg = self.proposal_target.sample(st)
-        self.keep_h.numpy()[...] = keep
-        self.fg_h.numpy()[...] = fg
+        self.keep_np[...] = keep
+        self.fg_np[...] = fg
         with torch.cuda.stream(s_src):
-            self.keep_d.copy_(self.keep_h, non_blocking=True)
-            self.fg_d.copy_(self.fg_h, non_blocking=True)
-            self.graphs["src2"].replay()
+            self.graphs["src2"].replay()  # starts with the upload of keep / fg from their pinned buffers
         with torch.cuda.stream(s_side):
-            at = self.anchor_target.finish_device(pending)
-            for dst, src in zip(self.at_static, at):
-                dst.copy_(src, non_blocking=True)
+            self.at_weights_np[...] = self.anchor_target.weights(pending["num_examples"])
             self.graphs["src3"].replay()
         with torch.cuda.stream(s_src):
             if copy_out is not None:
                 s_src.wait_stream(s_side)  # the source arena also carries the RPN / DA losses and anchor labels
                 copy_out("src", result)
+        # numpy's stream is where the next step will find it: generate the key blocks of the next anchor
+        # subsampling now, while the device works on src2
+        self.anchor_target.prefetch_stream(self.at_host.numel())
         for s in (s_src, s_tgt, s_side):
             cur.wait_stream(s)
         return result

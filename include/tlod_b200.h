@@ -332,6 +332,14 @@ int tlod_anchor_targets_finalize(const float* labels, const int* argmax, const f
                                  float* outside_w_out, int batch, int n, int k, int num_anchors,
                                  int height, int width, float inside_weight,
                                  float positive_weight, float negative_weight, void* stream);
+/* The same with {inside, positive, negative} weights read from DEVICE memory (3 floats): the
+ * positive / negative weight is 1 / (number of sampled anchors), known only after the host
+ * subsampling, so a launch captured in a CUDA graph cannot carry it as an argument. */
+int tlod_anchor_targets_finalize_dev(const float* labels, const int* argmax, const float* anchors,
+                                     const float* gt, int gt_stride, const int* inv_index,
+                                     float* labels_out, float* targets_out, float* inside_w_out,
+                                     float* outside_w_out, int batch, int n, int k, int num_anchors,
+                                     int height, int width, const float* weights_dev, void* stream);
 
 /* ------------------------------------------------------------------------ */
 /* Proposal-target assignment                              */

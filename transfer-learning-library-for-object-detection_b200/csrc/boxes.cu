@@ -229,7 +229,13 @@ __global__ void __launch_bounds__(256)
                            int gstride, const int* __restrict__ inv_index,
                            float* __restrict__ labels_out, float* __restrict__ targets_out,
                            float* __restrict__ inside_out, float* __restrict__ outside_out, int n,
-                           int k, int A, int H, int W, float inside_w, float pos_w, float neg_w) {
+                           int k, int A, int H, int W, float inside_w, float pos_w, float neg_w,
+                           const float* __restrict__ weights_dev) {
+  if (weights_dev) {  // {inside, positive, negative} in device memory (a captured launch cannot bake them in)
+    inside_w = __ldg(weights_dev);
+    pos_w = __ldg(weights_dev + 1);
+    neg_w = __ldg(weights_dev + 2);
+  }
   const int b = blockIdx.y;
   const int K = H * W;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;  // e = a * K + cell
@@ -432,14 +438,12 @@ extern "C" int tlod_anchor_labels(const float* anchors, const float* gt, int gt_
   return last_launch_status();
 }
 
-extern "C" int tlod_anchor_targets_finalize(const float* labels, const int* argmax,
-                                            const float* anchors, const float* gt, int gt_stride,
-                                            const int* inv_index, float* labels_out,
-                                            float* targets_out, float* inside_w_out,
-                                            float* outside_w_out, int batch, int n, int k,
-                                            int num_anchors, int height, int width,
-                                            float inside_weight, float positive_weight,
-                                            float negative_weight, void* stream) {
+static int anchor_targets_finalize(const float* labels, const int* argmax, const float* anchors, const float* gt,
+                                   int gt_stride, const int* inv_index, float* labels_out, float* targets_out,
+                                   float* inside_w_out, float* outside_w_out, int batch, int n, int k,
+                                   int num_anchors, int height, int width, float inside_weight,
+                                   float positive_weight, float negative_weight, const float* weights_dev,
+                                   void* stream) {
   if (!labels || !argmax || !anchors || !gt || !inv_index || !labels_out || !targets_out ||
       !inside_w_out || !outside_w_out)
     return TLOD_ERR_NULL_POINTER;
@@ -453,9 +457,33 @@ extern "C" int tlod_anchor_targets_finalize(const float* labels, const int* argm
     anchor_finalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
         labels, argmax, anchors, gt, gt_stride, inv_index, labels_out, targets_out, inside_w_out,
         outside_w_out, n, k, num_anchors, height, width, inside_weight, positive_weight,
-        negative_weight);
+        negative_weight, weights_dev);
   }
   return last_launch_status();
+}
+
+extern "C" int tlod_anchor_targets_finalize(const float* labels, const int* argmax,
+                                            const float* anchors, const float* gt, int gt_stride,
+                                            const int* inv_index, float* labels_out,
+                                            float* targets_out, float* inside_w_out,
+                                            float* outside_w_out, int batch, int n, int k,
+                                            int num_anchors, int height, int width,
+                                            float inside_weight, float positive_weight,
+                                            float negative_weight, void* stream) {
+  return anchor_targets_finalize(labels, argmax, anchors, gt, gt_stride, inv_index, labels_out, targets_out,
+                                 inside_w_out, outside_w_out, batch, n, k, num_anchors, height, width,
+                                 inside_weight, positive_weight, negative_weight, nullptr, stream);
+}
+
+extern "C" int tlod_anchor_targets_finalize_dev(const float* labels, const int* argmax, const float* anchors,
+                                                const float* gt, int gt_stride, const int* inv_index,
+                                                float* labels_out, float* targets_out, float* inside_w_out,
+                                                float* outside_w_out, int batch, int n, int k, int num_anchors,
+                                                int height, int width, const float* weights_dev, void* stream) {
+  if (!weights_dev) return TLOD_ERR_NULL_POINTER;
+  return anchor_targets_finalize(labels, argmax, anchors, gt, gt_stride, inv_index, labels_out, targets_out,
+                                 inside_w_out, outside_w_out, batch, n, k, num_anchors, height, width, 0.f, 0.f, 0.f,
+                                 weights_dev, stream);
 }
 
 extern "C" int tlod_roi_gt_assign(const float* rois, int roi_stride, int roi_offset, const float* gt,

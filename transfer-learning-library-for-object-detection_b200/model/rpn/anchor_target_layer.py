@@ -250,9 +250,12 @@ class _AnchorTargetLayer(nn.Module):
         # while the device still computes the labels: the MT19937 blocks the subsampling will draw
         # from (a permutation of the ~n background anchors per image, 1.33 words per draw on average)
         scratch = self._ahead  # per thread: DataParallel replicas share this module's attributes
-        ahead = pregenerate_stream(1.4 * labels_host.numel(), getattr(scratch, "buf", None))
-        if ahead is not None:
-            scratch.buf = ahead.base if ahead.base is not None else ahead
+        ahead = getattr(scratch, "ready", None)  # prefetch_stream(): generated in earlier idle time
+        scratch.ready = None
+        if ahead is None:
+            ahead = pregenerate_stream(1.4 * labels_host.numel(), getattr(scratch, "buf", None))
+            if ahead is not None:
+                scratch.buf = ahead.base if ahead.base is not None else ahead
         copied.synchronize()
         lab = labels_host.numpy()  # (B, n) fp32 in {-1, 0, 1}: edited in place on the host
 
@@ -261,20 +264,48 @@ class _AnchorTargetLayer(nn.Module):
         state["num_examples"] = subsample_labels(lab, num_fg, cfg.TRAIN.RPN_BATCHSIZE, ahead)
         return state
 
+    def prefetch_stream(self, labels_numel):
+        """Generate the MT19937 key blocks of the NEXT finish_host() now, in host time that would
+        otherwise be spent waiting for the device (e.g. after a step's last launch).  Safe at any time:
+        the blocks are dropped if anything draws from numpy's stream before they are used."""
+        scratch = self._ahead
+        ahead = pregenerate_stream(1.4 * labels_numel, getattr(scratch, "buf", None))
+        if ahead is not None:
+            scratch.buf = ahead.base if ahead.base is not None else ahead
+        scratch.ready = ahead
+
+    @staticmethod
+    def weights(num_examples):
+        """(inside, positive, negative) weights of :153-164 for the sampled-anchor count finish_host() left."""
+        inside_w = cfg.TRAIN.RPN_BBOX_INSIDE_WEIGHTS[0]
+        if cfg.TRAIN.RPN_POSITIVE_WEIGHT < 0:
+            # :155-158 -- num_examples of the LAST image (stale loop variable) for every image
+            positive_weights = 1.0 / num_examples if num_examples > 0 else float('inf')
+            return inside_w, positive_weights, positive_weights
+        assert ((cfg.TRAIN.RPN_POSITIVE_WEIGHT > 0) & (cfg.TRAIN.RPN_POSITIVE_WEIGHT < 1))
+        raise NotImplementedError("RPN_POSITIVE_WEIGHT >= 0 leaves the weights undefined in the "
+                                  "reference as well (anchor_target_layer.py:159-164)")
+
+    def launch_finalize(self, state, weights_host):
+        """The device half of finish() as pure launches on the CURRENT stream (capturable in a CUDA
+        graph): upload of the subsampled labels from state["labels_host"] and of the three weights from
+        the pinned (3,) fp32 tensor `weights_host` (the caller writes weights(num_examples) into it before
+        every replay), then the finalize kernel reading the weights from device memory."""
+        labels, argmax, anchors, inv_index = state["labels"], state["argmax"], state["anchors"], state["inv_index"]
+        gt_boxes = state["gt_boxes"]
+        weights_dev = torch.empty(3, dtype=torch.float32, device=gt_boxes.device)
+        weights_dev.copy_(weights_host, non_blocking=True)
+        labels.copy_(state["labels_host"], non_blocking=True)
+        return list(F.anchor_targets_finalize(labels, argmax, anchors, gt_boxes, inv_index, self._num_anchors,
+                                              state["height"], state["width"], 0.0, 0.0, 0.0,
+                                              weights_dev=weights_dev))
+
     def finish_device(self, state):
         labels, argmax, anchors, inv_index = state["labels"], state["argmax"], state["anchors"], state["inv_index"]
         gt_boxes, height, width = state["gt_boxes"], state["height"], state["width"]
         stream, labels_host, num_examples = state["stream"], state["labels_host"], state["num_examples"]
         A = self._num_anchors
-        inside_w = cfg.TRAIN.RPN_BBOX_INSIDE_WEIGHTS[0]
-        if cfg.TRAIN.RPN_POSITIVE_WEIGHT < 0:
-            # :155-158 -- num_examples of the LAST image (stale loop variable) for every image
-            positive_weights = 1.0 / num_examples if num_examples > 0 else float('inf')
-            negative_weights = positive_weights
-        else:
-            assert ((cfg.TRAIN.RPN_POSITIVE_WEIGHT > 0) & (cfg.TRAIN.RPN_POSITIVE_WEIGHT < 1))
-            raise NotImplementedError("RPN_POSITIVE_WEIGHT >= 0 leaves the weights undefined in the "
-                                      "reference as well (anchor_target_layer.py:159-164)")
+        inside_w, positive_weights, negative_weights = self.weights(num_examples)
 
         with torch.cuda.stream(stream):
             labels.copy_(labels_host, non_blocking=True)

@@ -71,6 +71,8 @@ SIGNATURES = {
     "tlod_numpy_permutation": (c_int, [P, ctypes.POINTER(c_int), c_longlong, P]),
     "tlod_anchor_targets_finalize": (c_int, [P, P, P, P, c_int, P, P, P, P, P, c_int, c_int, c_int, c_int,
                                              c_int, c_int, c_float, c_float, c_float, P]),
+    "tlod_anchor_targets_finalize_dev": (c_int, [P, P, P, P, c_int, P, P, P, P, P, c_int, c_int, c_int, c_int,
+                                                 c_int, c_int, P, P]),
     "tlod_roi_gt_assign": (c_int, [P, c_int, c_int, P, c_int, P, P, P, c_int, c_int, c_int, P]),
     "tlod_proposal_sample_host": (c_int, [P, c_int, c_int, c_int, c_int, c_float, c_float, c_float, P,
                                           ctypes.POINTER(c_int), P, P]),

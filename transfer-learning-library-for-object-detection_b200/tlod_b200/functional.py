@@ -434,8 +434,12 @@ def anchor_labels(anchors, gt_boxes, negative_overlap: float, positive_overlap: 
 
 
 def anchor_targets_finalize(labels, argmax, anchors, gt_boxes, inv_index, num_anchors: int, height: int,
-                            width: int, inside_weight: float, positive_weight: float, negative_weight: float):
-    _require_cuda(labels, argmax, anchors, gt_boxes, inv_index)
+                            width: int, inside_weight: float, positive_weight: float, negative_weight: float,
+                            weights_dev=None):
+    """weights_dev: optional (3,) fp32 device tensor {inside, positive, negative}; when given the three
+    float arguments are ignored (the launch can then be captured in a CUDA graph and replayed with
+    other weights)."""
+    _require_cuda(labels, argmax, anchors, gt_boxes, inv_index, weights_dev)
     labels, anchors, gt = _f32(labels), _f32(anchors), _f32(gt_boxes)
     argmax = argmax.contiguous()
     inv_index = inv_index.contiguous()
@@ -447,6 +451,16 @@ def anchor_targets_finalize(labels, argmax, anchors, gt_boxes, inv_index, num_an
     targets = torch.empty((B, 4 * A, H, W), dtype=torch.float32, device=dev)
     inside = torch.empty_like(targets)
     outside = torch.empty_like(targets)
+    if weights_dev is not None:
+        if weights_dev.dtype != torch.float32 or weights_dev.numel() != 3 or not weights_dev.is_contiguous():
+            raise ValueError("weights_dev must be a contiguous (3,) fp32 tensor")
+        with torch.cuda.device(dev):
+            check(lib.tlod_anchor_targets_finalize_dev(labels.data_ptr(), argmax.data_ptr(), anchors.data_ptr(),
+                                                       gt.data_ptr(), gs, inv_index.data_ptr(),
+                                                       labels_out.data_ptr(), targets.data_ptr(), inside.data_ptr(),
+                                                       outside.data_ptr(), B, N, K, A, H, W, weights_dev.data_ptr(),
+                                                       _stream(dev)), "tlod_anchor_targets_finalize_dev")
+        return labels_out, targets, inside, outside
     with torch.cuda.device(dev):
         check(lib.tlod_anchor_targets_finalize(labels.data_ptr(), argmax.data_ptr(), anchors.data_ptr(),
                                                gt.data_ptr(), gs, inv_index.data_ptr(), labels_out.data_ptr(),
