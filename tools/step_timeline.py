@@ -57,9 +57,7 @@ def one():
     hmark("anchor subsample done")
     st = self.static["src1"][1]
     st["copied"] = copied
-    keep, fg = self.proposal_target.sample(st)
-    self.keep_np[...] = keep
-    self.fg_np[...] = fg
+    self.proposal_target.sample(st, out=(self.keep_np, self.fg_np))
     hmark("proposal sampling done")
     with torch.cuda.stream(s_src):
         dmark("src2 start", s_src)

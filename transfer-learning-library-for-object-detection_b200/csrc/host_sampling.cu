@@ -242,7 +242,12 @@ void legacy_permutation_keep_last(Mt19937& rng, std::vector<int>& ident, std::ve
           above_lo |= _mm_movemask_ps(_mm_castsi128_ps(_mm_cmpgt_epi32(v, vlo))) << (4 * t);
           above_ii |= _mm_movemask_ps(_mm_castsi128_ps(_mm_cmpgt_epi32(v, vii))) << (4 * t);
         }
-        sure = 16u - (uint32_t)__builtin_popcount((unsigned)above_lo);
+        uint32_t pc = (uint32_t)above_lo;  // 16-bit population count (no POPCNT in the baseline ISA)
+        pc = pc - ((pc >> 1) & 0x5555u);
+        pc = (pc & 0x3333u) + ((pc >> 2) & 0x3333u);
+        pc = (pc + (pc >> 4)) & 0x0f0fu;
+        pc = (pc + (pc >> 8)) & 0x1fu;
+        sure = 16u - pc;
         unsure = (uint32_t)(above_lo & ~above_ii);
 #else
         for (int t = 0; t < 16; ++t) {
@@ -266,6 +271,22 @@ void legacy_permutation_keep_last(Mt19937& rng, std::vector<int>& ident, std::ve
   for (int k = 0; k < keep; ++k) out[k] = x[n - keep + k];
   for (int j : touched) x[j] = j;
   for (int k = n - keep; k < n; ++k) x[k] = k;
+}
+
+// lab[k] = -1 wherever lab[k] == +-0
+void disable_zeros(float* lab, int n) {
+  int k = 0;
+#if defined(__SSE2__)
+  const __m128i zero = _mm_setzero_si128();
+  const __m128i minus1 = _mm_castps_si128(_mm_set1_ps(-1.f));
+  for (; k + 4 <= n; k += 4) {
+    const __m128i x = _mm_loadu_si128(reinterpret_cast<const __m128i*>(lab + k));
+    const __m128i z = _mm_cmpeq_epi32(_mm_slli_epi32(x, 1), zero);
+    _mm_storeu_si128(reinterpret_cast<__m128i*>(lab + k), _mm_or_si128(_mm_andnot_si128(z, x), _mm_and_si128(z, minus1)));
+  }
+#endif
+  for (; k < n; ++k)
+    if (lab[k] == 0.f) lab[k] = -1.f;
 }
 
 }  // namespace
@@ -340,7 +361,7 @@ extern "C" int tlod_anchor_subsample_host_ahead(float* labels, int batch, int n,
       const int keep = num_bg > 0 ? num_bg : 0;
       kept.resize(keep);
       legacy_permutation_keep_last(rng, ident, touched, n_bg, keep, kept.data());
-      for (int k = 0; k < n_bg; ++k) lab[bgp[k]] = -1.f;
+      disable_zeros(lab, n);  // every background label -> -1 (one streaming pass), then the kept ones back
       for (int k = 0; k < keep; ++k) lab[bgp[kept[k]]] = 0.f;
       bg_kept = keep;
     }

@@ -13,8 +13,12 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+import ctypes
+
+from model.rpn.anchor_target_layer import _MT_WORDS, _numpy_mt19937_address
 from model.utils.config import cfg
 from tlod_b200 import functional as F
+from tlod_b200._lib import lib
 
 
 _native_ok = None
@@ -55,13 +59,18 @@ def _sample_numpy(mo, rois_per_image, fg_rois_per_image):
     return keep, fg_count
 
 
-def _sample_native(mo, rois_per_image, fg_rois_per_image):
-    from model.rpn.anchor_target_layer import _MT_WORDS, _numpy_mt19937_address
-    import ctypes
-    from tlod_b200._lib import lib
+def _sample_native(mo, rois_per_image, fg_rois_per_image, out=None):
+    """out: optional (keep (B, rois_per_image) int32, fg_count (B,) int32) C-contiguous numpy arrays
+    the samples are written into (e.g. views of pinned upload buffers)."""
     B, n = mo.shape
-    keep = np.empty((B, rois_per_image), np.int32)
-    fg_count = np.empty((B,), np.int32)
+    if out is None:
+        keep = np.empty((B, rois_per_image), np.int32)
+        fg_count = np.empty((B,), np.int32)
+    else:
+        keep, fg_count = out
+        if keep.shape != (B, rois_per_image) or fg_count.shape != (B,) or keep.dtype != np.int32 or \
+                fg_count.dtype != np.int32 or not keep.flags.c_contiguous or not fg_count.flags.c_contiguous:
+            raise ValueError("out must be C-contiguous int32 arrays of shapes (B, rois_per_image) and (B,)")
     addr = _numpy_mt19937_address()
     with np.random.mtrand._rand._bit_generator.lock:
         rc = lib.tlod_proposal_sample_host(mo.ctypes.data, B, n, rois_per_image, fg_rois_per_image,
@@ -76,7 +85,6 @@ def _sample_native(mo, rois_per_image, fg_rois_per_image):
 
 def _native_matches_numpy():
     """One-time self check on a private copy of the stream: same samples AND same stream position."""
-    from model.rpn.anchor_target_layer import _numpy_mt19937_address
     if _numpy_mt19937_address() is None:
         return False
     saved = np.random.get_state()
@@ -132,10 +140,11 @@ class _ProposalTargetLayer(nn.Module):
         return {"all_rois": all_rois, "gt_boxes": gt_boxes, "assignment": assignment, "labels": labels,
                 "host": host, "copied": copied}
 
-    def sample(self, state):
+    def sample(self, state, out=None):
         """Host-side fg / bg sampling, :140-181: same index order, same RNG calls.  Runs the native
         sampler (tlod_proposal_sample_host, on numpy's own MT19937 state) once it has been checked
-        against the numpy transcription below on this installation."""
+        against the numpy transcription below on this installation.  out: optional (keep, fg_count)
+        int32 numpy arrays to fill (see _sample_native)."""
         global _native_ok
         if state["copied"] is not None:
             state["copied"].synchronize()
@@ -147,8 +156,13 @@ class _ProposalTargetLayer(nn.Module):
         if _native_ok is None:
             _native_ok = _native_matches_numpy()
         if _native_ok and mo.dtype == np.float32 and mo.flags.c_contiguous:
-            return _sample_native(mo, rois_per_image, fg_rois_per_image)
-        return _sample_numpy(mo, rois_per_image, fg_rois_per_image)
+            return _sample_native(mo, rois_per_image, fg_rois_per_image, out)
+        keep, fg_count = _sample_numpy(mo, rois_per_image, fg_rois_per_image)
+        if out is not None:
+            out[0][...] = keep
+            out[1][...] = fg_count
+            return out
+        return keep, fg_count
 
     def finish(self, state, keep, fg_count):
         """keep (B, rois_per_image) / fg_count (B,): numpy arrays from sample(), or int32 device tensors
