@@ -331,18 +331,19 @@ class TlodStep(object):
                 arrived = torch.cuda.Event()
                 arrived.record(s_src)
                 s_side.wait_event(arrived)  # the anchor-target layer reads inputs this copy delivers
-        # two chains feed the host sampling: proposals + IoU (src1, ~150 us of device time) and the anchor
-        # labels (at1, ~35 us, then ~90 us of host subsampling): the longer device chain is queued first
-        with torch.cuda.stream(s_src):
-            self.graphs["src1"].replay()
-            copied = self.events["src1"]
-            copied.record(s_src)
+        # two chains feed the host sampling: the anchor labels (at1, ~35 us of device time, then ~90 us of
+        # host subsampling) and proposals + IoU (src1, ~125 us of device time): the one with the host part
+        # behind it is queued first
         with torch.cuda.stream(s_side):
             self.graphs["at1"].replay()
             pending = self.static["at1"]
             pending["copied"] = self.events["at1"]
             pending["copied"].record(s_side)
             pending["stream"] = s_side
+        with torch.cuda.stream(s_src):
+            self.graphs["src1"].replay()
+            copied = self.events["src1"]
+            copied.record(s_src)
         result = {"src": dict(self.static["src2"], **self.static["src3"]), "tgt": self.static["tgt"],
                   "anchor_targets": self.at_static}
         with torch.cuda.stream(s_tgt):

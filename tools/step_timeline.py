@@ -35,12 +35,6 @@ def one():
     hmark("start")
     for s in (s_src, s_tgt, s_side):
         s.wait_stream(cur)
-    with torch.cuda.stream(s_src):
-        self.graphs["src1"].replay()
-        copied = self.events["src1"]
-        copied.record(s_src)
-        dmark("src1 done", s_src)
-    hmark("src1 queued")
     with torch.cuda.stream(s_side):
         self.graphs["at1"].replay()
         pending = self.static["at1"]
@@ -49,6 +43,12 @@ def one():
         pending["stream"] = s_side
         dmark("at1 done", s_side)
     hmark("at1 queued")
+    with torch.cuda.stream(s_src):
+        self.graphs["src1"].replay()
+        copied = self.events["src1"]
+        copied.record(s_src)
+        dmark("src1 done", s_src)
+    hmark("src1 queued")
     with torch.cuda.stream(s_tgt):
         self.graphs["tgt"].replay()
         dmark("tgt done", s_tgt)

@@ -10,13 +10,14 @@
 //   1. proposal_sort_runs_kernel + proposal_rank_decode_kernel: sort by ranking of the
 //      (score desc, index asc) keys over many CTAs; only the pre_nms_topN best anchors are
 //      decoded + clipped, each written straight to its rank.
-//   2. nms_mask_kernel   upper-triangular 64x64 tiles of the IoU > thresh bitmask (fp32 ALU
-//      bound), computed in phases: only the leading S x S triangle the scan can reach before
-//      post_nms_topN boxes have survived, extended x4 only if the scan asks for it.
+//   2. nms_mask_kernel   lower-triangular 64x64 tiles of the IoU > thresh bitmask (fp32 ALU
+//      bound; row x holds the EARLIER boxes that overlap box x), computed in phases: only the
+//      leading S x S triangle the scan can reach before post_nms_topN boxes have survived,
+//      extended x4 only if the scan asks for it.
 //   3. nms_scan_kernel   one CTA per image: the greedy scan the reference runs on the host,
-//      done on chip: each 64-box chunk is resolved in a few warp-wide rounds, with a
-//      speculative prefetch of the diagonal and super-diagonal mask words; then the padded
-//      (post_nms_topN, 5) output.
+//      done on chip: warp 0 resolves each 64-box chunk in a few warp-wide rounds; twelve helper
+//      warps, one chunk each, AND the chunk's rows with the survivors of the earlier chunks;
+//      then the padded (post_nms_topN, 5) output.
 #include "common.cuh"
 
 namespace tlod {
@@ -60,7 +61,7 @@ __device__ __forceinline__ float4 load_box(const float* __restrict__ p, int stri
   return make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
 }
 
-// Mask layout, per image: word-major, mask[word j][row r] with rows padded to whole chunks --
+// Mask layout, per image: word-major, mask[word j][row r] (j <= r / 64: lower triangular) with rows padded to whole chunks --
 // the 64 rows of a chunk at one word are 512 contiguous bytes, so the scan fetches them with
 // fully coalesced loads.  (A row-major mask made every scan load a gather of one 32-byte sector
 // per lane: 32 tag lookups per instruction on the single SM that scans an image, ~2000 cycles
@@ -76,8 +77,8 @@ struct NmsState {
   int done;   // max_keep reached or every box examined: later phases exit at once
 };
 
-// Phase p covers the boxes [S_{p-1}, S_p).  Its mask kernel fills, for the column blocks of
-// the phase, the 64x64 tiles of all row blocks at or above the diagonal; the scan kernel then
+// Phase p covers the boxes [S_{p-1}, S_p).  Its mask kernel fills, for the row blocks of
+// the phase, the 64x64 tiles of all column blocks at or before the diagonal; the scan kernel then
 // continues the greedy scan over those boxes.  S_1 is sized so that the scan normally reaches
 // max_keep inside phase 1 (the IoU work is then S_1^2/2 pairs instead of n^2/2); if it does
 // not, the next phase is four times larger.  Later phases find `done` set and return.
@@ -94,7 +95,8 @@ __host__ __device__ inline int nms_phase_end(int n, int max_keep, int phase /* 1
 
 // Persistent grid (gridDim.x CTAs per image, blockIdx.y = image); 256 threads: thread t owns
 // row t & 63 of a 64x64 tile and 16 of its 64 columns (quarter t >> 6).  The tiles of a phase are the pairs
-// (col block cb in [cb0, cb1), row block rb <= cb), numbered cb-major.
+// (row block rb in [cb0, cb1), col block cb <= rb), numbered rb-major (the enumeration below finds
+// the pair as (larger, smaller) and swaps the roles).
 // mask[img][col_block][row] (np = padded rows); in the diagonal tile the word holds every other box of
 // the chunk that overlaps the row's box (both directions).
 template <bool FILTER>
@@ -129,7 +131,12 @@ __global__ void __launch_bounds__(256)
     int col_blk = (int)((sqrtf(8.f * (float)g + 1.f) - 1.f) * 0.5f);
     while ((long long)col_blk * (col_blk + 1) / 2 > g) --col_blk;
     while ((long long)(col_blk + 1) * (col_blk + 2) / 2 <= g) ++col_blk;
-    const int row_blk = (int)(g - (long long)col_blk * (col_blk + 1) / 2);
+    int row_blk = (int)(g - (long long)col_blk * (col_blk + 1) / 2);
+    {  // the scan wants the LOWER triangle: rows of the phase's chunks against the chunks at or before them
+      const int big = col_blk;
+      col_blk = row_blk;
+      row_blk = big;
+    }
     const int col_size = min(n - col_blk * 64, 64);
     const int row_size = min(n - row_blk * 64, 64);
     __syncthreads();  // previous tile's cbox readers
@@ -164,7 +171,7 @@ __global__ void __launch_bounds__(256)
 // ===========================================================================
 // greedy scan (one CTA per image and phase)
 // ===========================================================================
-constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_THREADS = 512;
 
 __device__ __forceinline__ unsigned long long shfl_u64(unsigned long long v, int src) {
   unsigned lo = __shfl_sync(0xffffffffu, (unsigned)v, src);
@@ -230,178 +237,213 @@ __device__ __forceinline__ unsigned long long resolve_chunk(unsigned long long c
   return kept;
 }
 
-// (Tried in round 2: feeding the loop through shared memory -- warp 0's words by one 2 KB
-// cp.async.bulk per chunk four chunks ahead, the helpers' rows by 512-byte bulk copies folded two
-// iterations later -- to take the L2 round trips out of the per-chunk barrier cycle.  Bit-exact,
-// but slower: 74 vs 64 us (ncu) for the 12000 -> 2000 scan of one image; issuing up to ten bulk
-// copies per helper warp and chunk from one lane costs more than the register prefetch it replaced.)
 // Continues the scan over the chunks [c0, c1) of one phase.
 // keep_out[img * keep_stride + r] = r-th kept index (ascending), num_out[img] = count
 // (<= max_keep).  If rois_out != NULL also writes the reference's padded
 // (post, 5) block for the image: column 0 = image index, rows [0, count) = boxes.
 //
-// Chunk c = boxes [64c, 64c+64).  Warp 0 resolves the chunks in order; the suppression
-// word of chunk c is
-//     remv[c]                      rows of survivors of chunks <= c-3   (other warps, below)
-//   | OR survivors(c-1) of mask[row][c]   "s1", prefetched by warp 0 before it knew the survivors
-//   | OR survivors(c-2) of mask[row][c]   "s2", likewise
-// The other 7 warps fold the rows of chunk c's survivors into remv[j >= c+3]: their loads are
-// issued in iteration c and OR-ed into lane-private partial words in iteration c+1; word j is
-// reduced across the lanes once, in iteration j-2, two barriers before warp 0 needs it.
+// The mask is LOWER triangular: the word of row x at word w <= x / 64 holds the boxes of chunk w
+// that overlap box x (the mask kernel computes the transposed tiles; IoU is symmetric bit for
+// bit).  Box x of chunk c is suppressed from outside its chunk iff
+//     OR_{w < c} ( mask[w][x] & kept[w] ) != 0          kept[w] = survivors of chunk w
+// -- a test every lane does on its own two rows: no cross-lane OR of 64-bit words (REDUX was the
+// longest item on the per-chunk chain of the first design, which pushed each chunk's surviving
+// rows into the words of all later chunks), no per-survivor selects, and nothing has to be
+// carried in from earlier phases except kept[] itself.
+//   * Warp 0 resolves the chunks in order.  The term w = c - 1 it evaluates itself (two ANDs and
+//     two ballots); its own mask words arrive two chunks ahead in registers.
+//   * The words w <= c - 2 of a chunk belong to ONE helper warp (helper h: chunks c0 + h, c0 + h + 12,
+//     ...).  It requests the chunk's rows sixteen words at a time and ANDs them with kept[w]; the
+//     newest words it polls for, the very last one (w = c - 2) while warp 0 works on chunk c - 1,
+//     and it publishes one 64-bit suppression word.  A helper is busy with its chunk for a few
+//     thousand cycles (an L2 round trip per batch); the twelve of them together deliver one chunk
+//     per ~300 cycles.
+//   * There is no CTA barrier in the loop: warp 0 publishes kept[c], the helpers their words,
+//     through shared memory as self-validating tagged words (below).
+// Measured (profiles/r02_nms_scan_variants.txt): 12000 -> 2000 boxes, 46 chunks: 55 -> 35 us per
+// image.  The designs that prefetched two or three chunks ahead INSIDE a warp (the round-1 kernel and
+// four rewrites) all ran at ~1.2 us per chunk whatever the distance: a warp has six scoreboards, so a
+// wait for the rows requested chunks ago also waits for the ones requested just now.
+// helper warps: 12 of the 16 -- warps 4, 8 and 12 stay idle so that warp 0 has its scheduler (SM
+// sub-partition = warp index mod 4) to itself: next to three polling helpers its ~40 instructions of
+// publish + emit took 443 cycles per chunk.  Helper h owns the chunks c0 + h, c0 + h + 12, ...
+constexpr int SCAN_HW = SCAN_THREADS / 32 - SCAN_THREADS / 128;
+constexpr int SCAN_BATCH = 16;                  // words a helper has in flight at a time (32 loads)
+constexpr int SCAN_RING = 8;                    // partial-word slots (a helper is at most 2 chunks ahead of warp 0)
+
+// Everything the warps hand to each other travels as SELF-VALIDATING 64-bit words: (tag << 32) | half,
+// tag = chunk + 1.  A 64-bit shared-memory store is single-copy atomic, so a reader that sees the
+// tag has the payload.
+__device__ __forceinline__ unsigned long long scan_pack(int tag, unsigned half) {
+  return ((unsigned long long)(unsigned)tag << 32) | half;
+}
+struct ScanShared {
+  unsigned long long partial[SCAN_RING][2];  // helper -> warp 0: suppression word of a chunk, two tagged halves
+  volatile int stop;                            // max_keep reached or the phase is over: helpers leave
+  int nkeep;                                    // survivors so far (capped)
+};
+
+// kept[w] (survivors of chunk w) once warp 0 has published it; false: the scan has stopped
+__device__ __forceinline__ bool scan_kept(const volatile unsigned long long* kp, const volatile int* stop, int w,
+                                          unsigned long long* out) {
+  unsigned long long a = kp[2 * w], b = kp[2 * w + 1];
+  while ((int)(a >> 32) != w + 1 || (int)(b >> 32) != w + 1) {
+    if (*stop) return false;
+    a = kp[2 * w];
+    b = kp[2 * w + 1];
+  }
+  *out = (b << 32) | (a & 0xffffffffULL);
+  return true;
+}
+
+// One helper warp, one chunk: which of the chunk's boxes (lane: rows lane and lane + 32) are suppressed by
+// survivors of the chunks <= c - 2.  SCAN_BATCH words are requested at a time and ANDed with kept[w] in
+// ascending order; only the last few words can still be unresolved (then the lane polls).  The latency
+// of the batches is hidden by the other 11 helpers working on the next chunks -- NOT by prefetching
+// several chunks ahead inside one warp: a warp has six scoreboards, so loads issued for later chunks
+// share a scoreboard with the ones being waited for, and every wait became a full L2 round trip
+// whatever the prefetch distance (the common ~1.2 us per chunk of all earlier versions).
+__device__ __forceinline__ bool scan_chunk(ScanShared& sh, const unsigned long long* __restrict__ m, int np,
+                                           const volatile unsigned long long* kp, int c, int lane) {
+  unsigned long long a0 = 0ULL, a1 = 0ULL;
+  const unsigned long long* rows = m + 64 * c + lane;
+  for (int wb = 0; wb <= c - 2; wb += SCAN_BATCH) {
+    if (sh.stop) return false;
+    unsigned long long v[SCAN_BATCH][2];
+#pragma unroll
+    for (int k = 0; k < SCAN_BATCH; ++k) {
+      const int w = wb + k;
+      v[k][0] = w <= c - 2 ? rows[(size_t)w * np] : 0ULL;
+      v[k][1] = w <= c - 2 ? rows[(size_t)w * np + 32] : 0ULL;
+    }
+    // optimistic: the batch's kept[] words are read together and their tags checked afterwards; a word
+    // that is not there yet (the newest one or two of the chunk) is polled for, in ascending order
+    unsigned long long lo_w[SCAN_BATCH], hi_w[SCAN_BATCH];
+#pragma unroll
+    for (int k = 0; k < SCAN_BATCH; ++k) {
+      const int w = wb + k <= c - 2 ? wb + k : 0;
+      lo_w[k] = kp[2 * w];
+      hi_w[k] = kp[2 * w + 1];
+    }
+#pragma unroll
+    for (int k = 0; k < SCAN_BATCH; ++k) {
+      const int w = wb + k;
+      if (w <= c - 2) {
+        unsigned long long km = (hi_w[k] << 32) | (lo_w[k] & 0xffffffffULL);
+        if ((int)(lo_w[k] >> 32) != w + 1 || (int)(hi_w[k] >> 32) != w + 1) {
+          if (!scan_kept(kp, &sh.stop, w, &km)) return false;
+        }
+        a0 |= v[k][0] & km;
+        a1 |= v[k][1] & km;
+      }
+    }
+  }
+  const unsigned lo = __ballot_sync(0xffffffffu, a0 != 0ULL), hi = __ballot_sync(0xffffffffu, a1 != 0ULL);
+  if (lane == 0) {
+    volatile unsigned long long* p = sh.partial[c % SCAN_RING];
+    p[0] = scan_pack(c + 1, lo);
+    p[1] = scan_pack(c + 1, hi);
+  }
+  return true;
+}
+
 __global__ void __launch_bounds__(SCAN_THREADS)
     nms_scan_kernel(const unsigned long long* __restrict__ mask, int n, int max_keep,
                     int* __restrict__ keep_out, int keep_stride, int* __restrict__ num_out,
                     const float* __restrict__ boxes, int box_stride, float* __restrict__ rois_out,
-                    int post, int c0, int c1, int last_phase, NmsState* __restrict__ state, int np) {
-  extern __shared__ unsigned long long remv[];  // ncb words (only [c0, c1) are used)
-  __shared__ unsigned long long kept_sh[2];
-  __shared__ int done_sh[2];
-  __shared__ int nkeep_sh;
+                    int post, int c0, int c1, int last_phase, NmsState* __restrict__ state, int np, int ncb) {
+  extern __shared__ unsigned long long kp_smem[];  // 2 * ncb tagged halves: survivors per chunk
+  volatile unsigned long long* kp = kp_smem;
+  __shared__ ScanShared sh;
   const int img = blockIdx.x;
   if (state[img].done) return;
-  const unsigned long long* m = mask + (size_t)img * nms_mask_words(n);  // m[word * np + row]
+  const unsigned long long* m = mask + (size_t)img * nms_mask_words(n);  // m[word * np + row], word <= row / 64
   int* keep = keep_out + (size_t)img * keep_stride;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int nkeep0 = state[img].nkeep;
 
-  // ---- carry-in: rows of the survivors of earlier phases, at the words of this phase ----
-  for (int j = c0 + wid; j < c1; j += SCAN_THREADS / 32) {
-    unsigned long long acc = 0ULL;
-    for (int k = lane; k < nkeep0; k += 32 * 4) {
-      unsigned long long v[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = (k + 32 * u < nkeep0) ? m[(size_t)j * np + keep[k + 32 * u]] : 0ULL;
-      acc |= v[0] | v[1] | v[2] | v[3];
-    }
-    acc = warp_or_u64(acc);
-    if (lane == 0) remv[j] = acc;
+  // ---- kept[] of the earlier phases, from the keep list (chunks of this phase: tag 0 = not resolved) ----
+  for (int j = tid; j < 2 * c1; j += SCAN_THREADS) kp_smem[j] = (j >> 1) < c0 ? scan_pack((j >> 1) + 1, 0u) : 0ULL;
+  if (tid < SCAN_RING * 2) (&sh.partial[0][0])[tid] = 0ULL;
+  if (tid == 0) sh.stop = 0;
+  __syncthreads();
+  for (int k = tid; k < nkeep0; k += SCAN_THREADS) {
+    const int idx = keep[k];
+    atomicOr(&kp_smem[2 * (idx >> 6) + ((idx >> 5) & 1)], 1ULL << (idx & 31));
   }
   __syncthreads();
 
-  // ---- warp 0 state ----
-  int nkeep = nkeep0;
-  unsigned long long d0 = 0, d1 = 0;      // diagonal words of the current chunk (rows lane, lane+32)
-  unsigned long long s1a = 0, s1b = 0;    // rows of chunk c-1 at word c
-  unsigned long long s2a = 0, s2b = 0;    // rows of chunk c-2 at word c
-  unsigned long long kept1 = 0ULL, kept2 = 0ULL;  // survivors of chunks c-1, c-2 (this phase)
-  if (wid == 0 && c0 < c1) {
-    if (64 * c0 + lane < n) d0 = m[(size_t)c0 * np + 64 * c0 + lane];
-    if (64 * c0 + lane + 32 < n) d1 = m[(size_t)c0 * np + 64 * c0 + lane + 32];
-  }
-  // ---- helper state ----
-  // Helper warp h (1..HW) owns the words c0 + (h-1) + u * HW, u < MAXW.  For every chunk it loads
-  // the chunk's 64 rows at its words (two coalesced 256-byte loads per word: lane l holds rows l
-  // and l + 32), ORs the survivors' rows into lane-private partial words one iteration later, and
-  // reduces a word across the lanes once, two barriers before warp 0 reads it (REDUX is scarce).
-  constexpr int HW = SCAN_THREADS / 32 - 1;  // helper warps
-  constexpr int MAXW = 10;                   // words per helper warp: HW * MAXW = 70 words per phase
-  unsigned long long pend[MAXW][2];          // loads in flight (issued in iteration c, folded in c + 1)
-  unsigned long long acc[MAXW];              // lane-private OR of the survivors' rows so far
-#pragma unroll
-  for (int u = 0; u < MAXW; ++u) acc[u] = 0ULL;
-  unsigned long long pend_kept = 0ULL;       // survivors of the chunk the pending loads belong to
-  int pend_c = -1;
-  for (int c = c0; c < c1; ++c) {
-    if (wid == 0) {
-      // prefetch everything chunk c+1 will need that does not depend on decisions
-      unsigned long long nd0 = 0, nd1 = 0, n1a = 0, n1b = 0, n2a = 0, n2b = 0;
-      if (c + 1 < c1) {  // then chunks <= c are full: all their rows exist
-        const int w1 = c + 1;
-        const int r0 = 64 * w1 + lane, r1 = r0 + 32;
-        if (r0 < n) nd0 = m[(size_t)w1 * np + r0];
-        if (r1 < n) nd1 = m[(size_t)w1 * np + r1];
-        n1a = m[(size_t)w1 * np + 64 * c + lane];
-        n1b = m[(size_t)w1 * np + 64 * c + 32 + lane];
-        if (c >= c0 + 1) {
-          n2a = m[(size_t)w1 * np + 64 * (c - 1) + lane];
-          n2b = m[(size_t)w1 * np + 64 * (c - 1) + 32 + lane];
+  if (wid == 0) {
+    // ---- warp 0: the chain ----
+    int nkeep = nkeep0;
+    unsigned long long kept1 = 0ULL;
+    if (c0 > 0) kept1 = (kp[2 * c0 - 1] << 32) | (kp[2 * c0 - 2] & 0xffffffffULL);
+    // words of chunk c (registers a), c + 1 (b), c + 2 (requested now): T = rows at word c - 1, d = diagonal
+    auto request = [&](int cc, unsigned long long& T0, unsigned long long& T1, unsigned long long& D0,
+                       unsigned long long& D1) {
+      T0 = T1 = D0 = D1 = 0ULL;
+      if (cc < c1) {
+        const int r0 = 64 * cc + lane, r1 = r0 + 32;
+        if (r0 < n) D0 = m[(size_t)cc * np + r0];
+        if (r1 < n) D1 = m[(size_t)cc * np + r1];
+        if (cc > 0) {
+          if (r0 < n) T0 = m[(size_t)(cc - 1) * np + r0];
+          if (r1 < n) T1 = m[(size_t)(cc - 1) * np + r1];
         }
       }
-      unsigned long long urgent = 0ULL;
-      if ((kept1 >> lane) & 1ULL) urgent |= s1a;
-      if ((kept1 >> (lane + 32)) & 1ULL) urgent |= s1b;
-      if ((kept2 >> lane) & 1ULL) urgent |= s2a;
-      if ((kept2 >> (lane + 32)) & 1ULL) urgent |= s2b;
-      urgent = warp_or_u64(urgent);
-      const unsigned long long cur = remv[c] | urgent;
+    };
+    unsigned long long aT0, aT1, aD0, aD1, bT0, bT1, bD0, bD1;
+    request(c0, aT0, aT1, aD0, aD1);
+    request(c0 + 1, bT0, bT1, bD0, bD1);
+    for (int c = c0; c < c1; ++c) {
+      unsigned long long nT0, nT1, nD0, nD1;
+      request(c + 2, nT0, nT1, nD0, nD1);
+      // suppression from the chunks <= c - 2: the helpers' partial words (lane hh polls helper hh's pair)
+      unsigned long long cur = 0ULL;
+      {
+        const volatile unsigned long long* p = sh.partial[c % SCAN_RING];
+        unsigned long long x = p[0], y = p[1];
+        while ((int)(x >> 32) != c + 1 || (int)(y >> 32) != c + 1) {
+          x = p[0];
+          y = p[1];
+        }
+        cur = (y << 32) | (x & 0xffffffffULL);
+      }
+      // ... and from chunk c - 1
+      cur |= ballot_u64((aT0 & kept1) != 0ULL, (aT1 & kept1) != 0ULL);
       const int rows = min(64, n - 64 * c);
       const unsigned long long valid = rows == 64 ? ~0ULL : ((1ULL << rows) - 1ULL);
-      const unsigned long long kept = resolve_chunk(~cur & valid, d0, d1, lane);
+      const unsigned long long kk = resolve_chunk(~cur & valid, aD0, aD1, lane);
+      if (lane == 0) {
+        kp[2 * c] = scan_pack(c + 1, (unsigned)kk);
+        kp[2 * c + 1] = scan_pack(c + 1, (unsigned)(kk >> 32));
+      }
       // emit indices (ascending) up to max_keep
-      if ((kept >> lane) & 1ULL) {
-        const int r = nkeep + __popcll(kept & ((1ULL << lane) - 1ULL));
+      if ((kk >> lane) & 1ULL) {
+        const int r = nkeep + __popcll(kk & ((1ULL << lane) - 1ULL));
         if (r < max_keep) keep[r] = 64 * c + lane;
       }
-      if ((kept >> (lane + 32)) & 1ULL) {
-        const int r = nkeep + __popcll(kept & ((1ULL << (lane + 32)) - 1ULL));
+      if ((kk >> (lane + 32)) & 1ULL) {
+        const int r = nkeep + __popcll(kk & ((1ULL << (lane + 32)) - 1ULL));
         if (r < max_keep) keep[r] = 64 * c + lane + 32;
       }
-      nkeep += __popcll(kept);
-      if (lane == 0) {
-        kept_sh[c & 1] = kept;
-        done_sh[c & 1] = (nkeep >= max_keep) ? 1 : 0;
-      }
-      kept2 = kept1;
-      kept1 = kept;
-      d0 = nd0; d1 = nd1;
-      s1a = n1a; s1b = n1b; s2a = n2a; s2b = n2b;
+      nkeep += __popcll(kk);
+      if (nkeep >= max_keep) break;
+      kept1 = kk;
+      aT0 = bT0; aT1 = bT1; aD0 = bD0; aD1 = bD1;
+      bT0 = nT0; bT1 = nT1; bD0 = nD0; bD1 = nD1;
     }
-    __syncthreads();
-    if (done_sh[c & 1]) break;
-    if (wid != 0) {
-      const int h = wid - 1;
-      // 1. the rows loaded one iteration ago (chunk c-1), masked by that chunk's survivors
-      if (pend_c >= 0) {
-        const bool s0 = (pend_kept >> lane) & 1ULL, s1 = (pend_kept >> (lane + 32)) & 1ULL;
-#pragma unroll
-        for (int u = 0; u < MAXW; ++u) acc[u] |= (s0 ? pend[u][0] : 0ULL) | (s1 ? pend[u][1] : 0ULL);
-        pend_c = -1;
-      }
-      // 2. word c + 2 now holds the survivors of every chunk <= c - 1 (those of chunks c, c + 1
-      //    reach it through warp 0's s1 / s2 path): reduce it across the lanes, once
-      {
-        const int j = c + 2, rel = j - c0;
-        if (j < c1 && rel % HW == h && rel / HW < MAXW) {
-          const int uo = rel / HW;
-          unsigned long long v = 0ULL;
-#pragma unroll
-          for (int u = 0; u < MAXW; ++u)
-            if (u == uo) v = acc[u];
-          v = warp_or_u64(v);
-          if (lane == 0) remv[j] |= v;
-        }
-      }
-      // 3. rows of chunk c at this warp's words >= c + 3 (the rows exist: c + 3 < c1)
-      const unsigned long long k = kept_sh[c & 1];
-      if (k && c + 3 < c1) {
-        const unsigned long long* rows = m + 64 * c + lane;
-#pragma unroll
-        for (int u = 0; u < MAXW; ++u) {
-          const int j = c0 + h + u * HW;
-          pend[u][0] = 0ULL;
-          pend[u][1] = 0ULL;
-          if (j >= c + 3 && j < c1) {
-            pend[u][0] = rows[(size_t)j * np];
-            pend[u][1] = rows[(size_t)j * np + 32];
-          }
-        }
-        pend_c = c;
-        pend_kept = k;
-        // phases wider than HW * MAXW = 70 words: the rest, reduced per chunk
-        const bool s0 = (k >> lane) & 1ULL, s1 = (k >> (lane + 32)) & 1ULL;
-        for (int j = c0 + h + MAXW * HW; j < c1; j += HW) {
-          if (j < c + 3) continue;
-          const unsigned long long w = (s0 ? rows[(size_t)j * np] : 0ULL) | (s1 ? rows[(size_t)j * np + 32] : 0ULL);
-          const unsigned long long v = warp_or_u64(w);
-          if (lane == 0) remv[j] |= v;
-        }
-      }
+    if (lane == 0) {
+      sh.stop = 1;
+      sh.nkeep = min(nkeep, max_keep);
     }
+  } else if ((wid & 3) != 0) {
+    // ---- helpers ----
+    for (int c = c0 + (wid - 1 - wid / 4); c < c1; c += SCAN_HW)
+      if (!scan_chunk(sh, m, np, kp, c, lane)) break;
   }
   __syncthreads();
-  if (tid == 0) nkeep_sh = min(nkeep, max_keep);  // nkeep lives in warp 0 only
-  __syncthreads();
-  const int cnt = nkeep_sh;
+  const int cnt = sh.nkeep;
   const bool finished = cnt >= max_keep || last_phase;
   if (tid == 0) {
     state[img].nkeep = cnt;
@@ -411,14 +453,29 @@ __global__ void __launch_bounds__(SCAN_THREADS)
   if (finished && rois_out) {
     float* o = rois_out + (size_t)img * post * 5;
     const float* bx = boxes + (size_t)img * n * box_stride;
-    for (int r = tid; r < post; r += SCAN_THREADS) {
-      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < cnt) b = load_box(bx + (size_t)keep[r] * box_stride, box_stride);
-      o[r * 5 + 0] = (float)img;
-      o[r * 5 + 1] = b.x;
-      o[r * 5 + 2] = b.y;
-      o[r * 5 + 3] = b.z;
-      o[r * 5 + 4] = b.w;
+    // four rows per thread and pass: the index and box loads of a pass are all in flight together
+    for (int r0 = tid; r0 < post; r0 += 4 * SCAN_THREADS) {
+      int idx[4];
+      float4 b[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r = r0 + q * SCAN_THREADS;
+        idx[q] = r < cnt ? keep[r] : -1;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        b[q] = idx[q] >= 0 ? load_box(bx + (size_t)idx[q] * box_stride, box_stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r = r0 + q * SCAN_THREADS;
+        if (r < post) {
+          o[r * 5 + 0] = (float)img;
+          o[r * 5 + 1] = b[q].x;
+          o[r * 5 + 2] = b[q].y;
+          o[r * 5 + 3] = b[q].z;
+          o[r * 5 + 4] = b[q].w;
+        }
+      }
     }
   }
 }
@@ -757,15 +814,17 @@ static int launch_mask_scan(const float* boxes, int batch, int n, int stride, fl
     {
       // ncb * 8 bytes of dynamic shared memory: beyond 48 KB (n > 393 K boxes) opt in, beyond the
       // device limit refuse instead of failing the launch
-      if ((size_t)ncb * 8 > 48 * 1024) {
-        if ((size_t)ncb * 8 > (size_t)device_info().max_smem_optin) return TLOD_ERR_UNSUPPORTED;
-        cudaError_t e = cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ncb * 8);
+      const size_t scan_smem = (size_t)ncb * 16;  // kept[]: two tagged halves per chunk
+      if (scan_smem > 48 * 1024) {
+        if (scan_smem > (size_t)device_info().max_smem_optin) return TLOD_ERR_UNSUPPORTED;
+        cudaError_t e = cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)scan_smem);
         if (e != cudaSuccess) return (int)e;
       }
       LaunchScope scope("nms_scan_kernel", st);
-      nms_scan_kernel<<<batch, SCAN_THREADS, (size_t)ncb * 8, st>>>(mask, n, max_keep, keep, keep_stride, num,
-                                                                  boxes, stride, rois_out, post, c0, c1,
-                                                                  end >= n, state, np);
+      nms_scan_kernel<<<batch, SCAN_THREADS, scan_smem, st>>>(mask, n, max_keep, keep, keep_stride, num, boxes,
+                                                              stride, rois_out, post, c0, c1, end >= n, state, np,
+                                                              ncb);
     }
     rc = last_launch_status();
     if (rc) return rc;
