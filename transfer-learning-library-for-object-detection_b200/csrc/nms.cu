@@ -812,7 +812,7 @@ static int launch_mask_scan(const float* boxes, int batch, int n, int stride, fl
     int rc = last_launch_status();
     if (rc) return rc;
     {
-      // ncb * 8 bytes of dynamic shared memory: beyond 48 KB (n > 393 K boxes) opt in, beyond the
+      // ncb * 16 bytes of dynamic shared memory: beyond 48 KB (n > 196 K boxes) opt in, beyond the
       // device limit refuse instead of failing the launch
       const size_t scan_smem = (size_t)ncb * 16;  // kept[]: two tagged halves per chunk
       if (scan_smem > 48 * 1024) {
