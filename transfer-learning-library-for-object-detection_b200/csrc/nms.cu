@@ -15,7 +15,7 @@
 //      leading S x S triangle the scan can reach before post_nms_topN boxes have survived,
 //      extended x4 only if the scan asks for it.
 //   3. nms_scan_kernel   one CTA per image: the greedy scan the reference runs on the host,
-//      done on chip: warp 0 resolves each 64-box chunk in a few warp-wide rounds; twelve helper
+//      done on chip: warp 0 resolves each 64-box chunk in a few warp-wide rounds; eleven helper
 //      warps, one chunk each, AND the chunk's rows with the survivors of the earlier chunks;
 //      then the padded (post_nms_topN, 5) output.
 #include "common.cuh"
@@ -251,12 +251,13 @@ __device__ __forceinline__ unsigned long long resolve_chunk(unsigned long long c
 // rows into the words of all later chunks), no per-survivor selects, and nothing has to be
 // carried in from earlier phases except kept[] itself.
 //   * Warp 0 resolves the chunks in order.  The term w = c - 1 it evaluates itself (two ANDs and
-//     two ballots); its own mask words arrive two chunks ahead in registers.
-//   * The words w <= c - 2 of a chunk belong to ONE helper warp (helper h: chunks c0 + h, c0 + h + 12,
+//     two ballots); its own mask words arrive three chunks ahead through a cp.async ring.  The keep
+//     list is written by another warp (the emitter) from kept[].
+//   * The words w <= c - 2 of a chunk belong to ONE helper warp (helper h: chunks c0 + h, c0 + h + 11,
 //     ...).  It requests the chunk's rows sixteen words at a time and ANDs them with kept[w]; the
 //     newest words it polls for, the very last one (w = c - 2) while warp 0 works on chunk c - 1,
 //     and it publishes one 64-bit suppression word.  A helper is busy with its chunk for a few
-//     thousand cycles (an L2 round trip per batch); the twelve of them together deliver one chunk
+//     thousand cycles (an L2 round trip per batch); the eleven of them together deliver one chunk
 //     per ~300 cycles.
 //   * There is no CTA barrier in the loop: warp 0 publishes kept[c], the helpers their words,
 //     through shared memory as self-validating tagged words (below).
@@ -264,10 +265,10 @@ __device__ __forceinline__ unsigned long long resolve_chunk(unsigned long long c
 // image.  The designs that prefetched two or three chunks ahead INSIDE a warp (the round-1 kernel and
 // four rewrites) all ran at ~1.2 us per chunk whatever the distance: a warp has six scoreboards, so a
 // wait for the rows requested chunks ago also waits for the ones requested just now.
-// helper warps: 12 of the 16 -- warps 4, 8 and 12 stay idle so that warp 0 has its scheduler (SM
+// helper warps: 11 of the 16 -- warp 1 writes the keep list, warps 4, 8 and 12 stay idle so that warp 0 has its scheduler (SM
 // sub-partition = warp index mod 4) to itself: next to three polling helpers its ~40 instructions of
-// publish + emit took 443 cycles per chunk.  Helper h owns the chunks c0 + h, c0 + h + 12, ...
-constexpr int SCAN_HW = SCAN_THREADS / 32 - SCAN_THREADS / 128;
+// publish + emit took 443 cycles per chunk.  Helper h owns the chunks c0 + h, c0 + h + 11, ...
+constexpr int SCAN_HW = SCAN_THREADS / 32 - SCAN_THREADS / 128 - 1;  // 11: warp 1 writes the keep list
 constexpr int SCAN_BATCH = 16;                  // words a helper has in flight at a time (32 loads)
 constexpr int SCAN_RING = 8;                    // partial-word slots (a helper is at most 2 chunks ahead of warp 0)
 
@@ -280,7 +281,9 @@ __device__ __forceinline__ unsigned long long scan_pack(int tag, unsigned half) 
 struct ScanShared {
   unsigned long long partial[SCAN_RING][2];  // helper -> warp 0: suppression word of a chunk, two tagged halves
   volatile int stop;                            // max_keep reached or the phase is over: helpers leave
+  alignas(16) unsigned long long stage[4][32][4];  // warp 0's own mask words, four chunks in flight (cp.async)
   int nkeep;                                    // survivors so far (capped)
+  volatile int c_end;                           // chunks [c0, c_end) were resolved in this phase
 };
 
 // kept[w] (survivors of chunk w) once warp 0 has published it; false: the scan has stopped
@@ -296,10 +299,20 @@ __device__ __forceinline__ bool scan_kept(const volatile unsigned long long* kp,
   return true;
 }
 
+__device__ __forceinline__ unsigned long long scan_ldg(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ void scan_cp_async8(unsigned dst, const unsigned long long* src, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(valid ? 8 : 0) : "memory");
+}
+
 // One helper warp, one chunk: which of the chunk's boxes (lane: rows lane and lane + 32) are suppressed by
 // survivors of the chunks <= c - 2.  SCAN_BATCH words are requested at a time and ANDed with kept[w] in
 // ascending order; only the last few words can still be unresolved (then the lane polls).  The latency
-// of the batches is hidden by the other 11 helpers working on the next chunks -- NOT by prefetching
+// of the batches is hidden by the other 10 helpers working on the next chunks -- NOT by prefetching
 // several chunks ahead inside one warp: a warp has six scoreboards, so loads issued for later chunks
 // share a scoreboard with the ones being waited for, and every wait became a full L2 round trip
 // whatever the prefetch distance (the common ~1.2 us per chunk of all earlier versions).
@@ -310,11 +323,13 @@ __device__ __forceinline__ bool scan_chunk(ScanShared& sh, const unsigned long l
   for (int wb = 0; wb <= c - 2; wb += SCAN_BATCH) {
     if (sh.stop) return false;
     unsigned long long v[SCAN_BATCH][2];
+    // `asm volatile` loads: issued HERE, before the polls below.  With plain loads the compiler sinks
+    // them to their first use, behind the wait for kept[w] -- one L2 round trip per chunk on the chain.
 #pragma unroll
     for (int k = 0; k < SCAN_BATCH; ++k) {
-      const int w = wb + k;
-      v[k][0] = w <= c - 2 ? rows[(size_t)w * np] : 0ULL;
-      v[k][1] = w <= c - 2 ? rows[(size_t)w * np + 32] : 0ULL;
+      const int w = wb + k <= c - 2 ? wb + k : 0;
+      v[k][0] = scan_ldg(rows + (size_t)w * np);
+      v[k][1] = scan_ldg(rows + (size_t)w * np + 32);
     }
     // optimistic: the batch's kept[] words are read together and their tags checked afterwards; a word
     // that is not there yet (the newest one or two of the chunk) is polled for, in ascending order
@@ -378,27 +393,34 @@ __global__ void __launch_bounds__(SCAN_THREADS)
     int nkeep = nkeep0;
     unsigned long long kept1 = 0ULL;
     if (c0 > 0) kept1 = (kp[2 * c0 - 1] << 32) | (kp[2 * c0 - 2] & 0xffffffffULL);
-    // words of chunk c (registers a), c + 1 (b), c + 2 (requested now): T = rows at word c - 1, d = diagonal
-    auto request = [&](int cc, unsigned long long& T0, unsigned long long& T1, unsigned long long& D0,
-                       unsigned long long& D1) {
-      T0 = T1 = D0 = D1 = 0ULL;
-      if (cc < c1) {
-        const int r0 = 64 * cc + lane, r1 = r0 + 32;
-        if (r0 < n) D0 = m[(size_t)cc * np + r0];
-        if (r1 < n) D1 = m[(size_t)cc * np + r1];
-        if (cc > 0) {
-          if (r0 < n) T0 = m[(size_t)(cc - 1) * np + r0];
-          if (r1 < n) T1 = m[(size_t)(cc - 1) * np + r1];
-        }
-      }
+    const unsigned stage_addr = (unsigned)__cvta_generic_to_shared(&sh.stage[0][0][0]);
+    // Warp 0's own mask words -- T = this lane's rows at word c - 1, D = at the diagonal word c -- travel
+    // through a 4-slot shared-memory ring by cp.async, three chunks ahead.  Plain loads into rotating
+    // registers do not work here: a warp has six scoreboards, the compiler lets the load requested in this
+    // iteration share one with the load consumed in it, and every third chunk then waited a full L2 round
+    // trip (clock64: 650 of ~900 cycles).  cp.async.wait_group waits for the OLDEST group only.
+    auto request = [&](int cc) {
+      const int r0 = 64 * cc + lane, r1 = r0 + 32;
+      const unsigned dst = stage_addr + (unsigned)((cc & 3) * 1024 + lane * 32);
+      const bool in = cc < c1;
+      const unsigned long long* d0 = m + (size_t)(in ? cc : 0) * np + (in && r0 < n ? r0 : 0);
+      const unsigned long long* d1 = m + (size_t)(in ? cc : 0) * np + (in && r1 < n ? r1 : 0);
+      const unsigned long long* t0 = m + (size_t)(in && cc > 0 ? cc - 1 : 0) * np + (in && r0 < n ? r0 : 0);
+      const unsigned long long* t1 = m + (size_t)(in && cc > 0 ? cc - 1 : 0) * np + (in && r1 < n ? r1 : 0);
+      // src-size 0 = zero fill (rows past n, chunk 0 has no word c - 1, chunks past the phase)
+      scan_cp_async8(dst, t0, in && cc > 0 && r0 < n);
+      scan_cp_async8(dst + 8, t1, in && cc > 0 && r1 < n);
+      scan_cp_async8(dst + 16, d0, in && r0 < n);
+      scan_cp_async8(dst + 24, d1, in && r1 < n);
+      asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    unsigned long long aT0, aT1, aD0, aD1, bT0, bT1, bD0, bD1;
-    request(c0, aT0, aT1, aD0, aD1);
-    request(c0 + 1, bT0, bT1, bD0, bD1);
+    request(c0);
+    request(c0 + 1);
+    request(c0 + 2);
+    int c_end = c1;
     for (int c = c0; c < c1; ++c) {
-      unsigned long long nT0, nT1, nD0, nD1;
-      request(c + 2, nT0, nT1, nD0, nD1);
-      // suppression from the chunks <= c - 2: the helpers' partial words (lane hh polls helper hh's pair)
+      request(c + 3);
+      // suppression from the chunks <= c - 2: the helper's word
       unsigned long long cur = 0ULL;
       {
         const volatile unsigned long long* p = sh.partial[c % SCAN_RING];
@@ -409,16 +431,52 @@ __global__ void __launch_bounds__(SCAN_THREADS)
         }
         cur = (y << 32) | (x & 0xffffffffULL);
       }
+      asm volatile("cp.async.wait_group 3;" ::: "memory");  // the group of chunk c (three younger ones may be pending)
+      unsigned long long T0, T1, D0, D1;
+      {
+        const unsigned src = stage_addr + (unsigned)((c & 3) * 1024 + lane * 32);
+        asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(T0), "=l"(T1) : "r"(src));
+        asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(D0), "=l"(D1) : "r"(src + 16));
+      }
       // ... and from chunk c - 1
-      cur |= ballot_u64((aT0 & kept1) != 0ULL, (aT1 & kept1) != 0ULL);
+      cur |= ballot_u64((T0 & kept1) != 0ULL, (T1 & kept1) != 0ULL);
       const int rows = min(64, n - 64 * c);
       const unsigned long long valid = rows == 64 ? ~0ULL : ((1ULL << rows) - 1ULL);
-      const unsigned long long kk = resolve_chunk(~cur & valid, aD0, aD1, lane);
+      const unsigned long long kk = resolve_chunk(~cur & valid, D0, D1, lane);
       if (lane == 0) {
         kp[2 * c] = scan_pack(c + 1, (unsigned)kk);
         kp[2 * c + 1] = scan_pack(c + 1, (unsigned)(kk >> 32));
       }
-      // emit indices (ascending) up to max_keep
+      // (the keep list is written by the emitter warp, from kept[])
+      nkeep += __popcll(kk);
+      kept1 = kk;
+      if (nkeep >= max_keep) {
+        c_end = c + 1;
+        break;
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (lane == 0) {
+      sh.nkeep = min(nkeep, max_keep);
+      sh.c_end = c_end;
+      sh.stop = 1;
+    }
+  } else if (wid == 1) {
+    // ---- emitter: the keep list (ascending, up to max_keep) from kept[], off warp 0's chain ----
+    int nkeep = nkeep0;
+    for (int c = c0; c < c1; ++c) {
+      unsigned long long a = kp[2 * c], b = kp[2 * c + 1];
+      bool there = true;
+      while ((int)(a >> 32) != c + 1 || (int)(b >> 32) != c + 1) {
+        if (sh.stop && c >= sh.c_end) {  // stop is written after c_end and after the last kept[] word
+          there = false;
+          break;
+        }
+        a = kp[2 * c];
+        b = kp[2 * c + 1];
+      }
+      if (!there) break;
+      const unsigned long long kk = (b << 32) | (a & 0xffffffffULL);
       if ((kk >> lane) & 1ULL) {
         const int r = nkeep + __popcll(kk & ((1ULL << lane) - 1ULL));
         if (r < max_keep) keep[r] = 64 * c + lane;
@@ -429,17 +487,10 @@ __global__ void __launch_bounds__(SCAN_THREADS)
       }
       nkeep += __popcll(kk);
       if (nkeep >= max_keep) break;
-      kept1 = kk;
-      aT0 = bT0; aT1 = bT1; aD0 = bD0; aD1 = bD1;
-      bT0 = nT0; bT1 = nT1; bD0 = nD0; bD1 = nD1;
-    }
-    if (lane == 0) {
-      sh.stop = 1;
-      sh.nkeep = min(nkeep, max_keep);
     }
   } else if ((wid & 3) != 0) {
     // ---- helpers ----
-    for (int c = c0 + (wid - 1 - wid / 4); c < c1; c += SCAN_HW)
+    for (int c = c0 + (wid - 2 - wid / 4); c < c1; c += SCAN_HW)
       if (!scan_chunk(sh, m, np, kp, c, lane)) break;
   }
   __syncthreads();
