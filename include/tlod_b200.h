@@ -391,7 +391,9 @@ int tlod_grl_backward_weighted(const float* grad, const float* row_weight, float
  * ins_label (num_ins) or NULL (= domain_label everywhere), domain_label 0/1.
  * losses_out[4] = { image NLL (mean), instance BCE (mean), consistency MSE
  * (sum, target = mean softmax prob of channel domain_label, detached),
- * consistency target }.  workspace: tlod_da_loss_workspace_bytes(). */
+ * consistency target }.  workspace (tlod_da_loss_workspace_bytes(), 8-byte aligned) may be NULL:
+ * it is only used when the map has more than 2^16 cells, to reduce the image head over many
+ * CTAs first; without it such a map is reduced by one CTA (same result, slower). */
 size_t tlod_da_loss_workspace_bytes(void);
 int tlod_da_loss_forward(const float* img_score, const float* ins_prob, const float* ins_label,
                          int domain_label, float* losses_out, int batch, int height, int width,
