@@ -33,7 +33,10 @@ def _sorted_dets(n, seed, spread=900.0, jitter=False):
 
 @pytest.mark.parametrize("n,thresh,jitter", [(1, 0.7, False), (63, 0.7, False), (64, 0.5, True), (65, 0.3, True),
                                              (300, 0.3, True), (1000, 0.5, False), (6000, 0.7, True),
-                                             (12000, 0.7, False), (12000, 0.7, True), (4097, 0.0, False)])
+                                             (12000, 0.7, False), (12000, 0.7, True), (4097, 0.0, False),
+                                             # 313 chunks, every phase, helper batches of up to 20 rounds; few
+                                             # survivors per chunk at a low threshold
+                                             (20000, 0.7, True), (8000, 0.1, True)])
 def test_nms_keep_indices_bit_exact(n, thresh, jitter):
     from model.nms.nms_wrapper import nms
     dets = _sorted_dets(n, 100 + n, jitter=jitter)
